@@ -1,0 +1,182 @@
+// dense.cu -- see dense.h.  Straightforward single-CTA column algorithms; exactness matters more than speed
+// here (systems are small and replicated on every GPU).
+#include "dense.h"
+
+namespace bnl {
+namespace {
+
+constexpr int kDT = 1024;
+
+// In-place lower Cholesky of the dim x dim column-major matrix S (leading dim lds).  Sets *fail on a pivot <= 0.
+__device__ void chol_inplace(double* S, int dim, int lds, int* fail) {
+    for (int k = 0; k < dim; ++k) {
+        __syncthreads();
+        const double akk = S[(size_t)k * lds + k];
+        if (!(akk > 0.0)) {
+            if (threadIdx.x == 0) *fail = 1;
+            return;  // uniform: every thread reads the same akk
+        }
+        const double lkk = sqrt(akk);
+        __syncthreads();
+        for (int i = k + threadIdx.x; i < dim; i += blockDim.x) {
+            const double v = S[(size_t)k * lds + i];
+            S[(size_t)k * lds + i] = (i == k) ? lkk : v / lkk;
+        }
+        __syncthreads();
+        // trailing update: S[i][j] -= L[i][k] * L[j][k] for k < j <= i
+        const int rem = dim - k - 1;
+        const long long tot = (long long)rem * rem;
+        for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
+            const int jj = (int)(e / rem), ii = (int)(e % rem);
+            if (ii >= jj) {
+                const int i = k + 1 + ii, j = k + 1 + jj;
+                S[(size_t)j * lds + i] -= S[(size_t)k * lds + i] * S[(size_t)k * lds + j];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void k_chol_aat(DenseCtx c) {
+    const int m = c.m;
+    // LA = A A' (lower), then factor
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int j = e / m, i = e % m;
+        double s = 0.0;
+        if (i >= j) {
+            for (int k = 0; k < c.n; ++k) s = fma(c.A[(size_t)i * c.ld + k], c.A[(size_t)j * c.ld + k], s);
+        }
+        c.LA[(size_t)j * m + i] = s;
+    }
+    __syncthreads();
+    chol_inplace(c.LA, m, m, &c.sd->chol_fail);
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {  // zero the strict upper triangle
+        const int j = e / m, i = e % m;
+        if (i < j) c.LA[(size_t)j * m + i] = 0.0;
+    }
+}
+
+// cholesky_aug_aat (src/polyhedral_constraints.jl:35-59): fixidx = findall(fix); G = L_A \ A[:,fix];
+// S = I - G'G; L = [L_A 0; G' chol(S)]
+__global__ void k_rebuild(DenseCtx c, const unsigned char* fix) {
+    __shared__ int warp_cnt[32];
+    __shared__ int base;
+    const int m = c.m, cap = c.cap;
+    // ---- findall(fix), ascending ----
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int start = 0; start < c.n; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const bool f = (i < c.n) && fix[i];
+        const unsigned msk = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_cnt[warp] = __popc(msk);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+        if (f) c.fixidx[off + __popc(msk & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < nw; ++w) t += warp_cnt[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    const int q = base;
+    if (threadIdx.x == 0) {
+        *c.q_dev = q;
+        c.sd->nb_fix = q;
+    }
+    // ---- G = L_A \ A[:,fix]  (one thread per column, forward substitution) ----
+    for (int k = threadIdx.x; k < q; k += blockDim.x) {
+        const long long col = c.fixidx[k];
+        for (int i = 0; i < m; ++i) {
+            double s = c.A[(size_t)i * c.ld + col];
+            for (int j = 0; j < i; ++j) s -= c.LA[(size_t)j * m + i] * c.G[(size_t)k * m + j];
+            c.G[(size_t)k * m + i] = s / c.LA[(size_t)i * m + i];
+        }
+    }
+    __syncthreads();
+    // ---- assemble L: top-left L_A, bottom-left G', bottom-right S = I - G'G (lower) ----
+    const int mpp = m + q;
+    for (long long e = threadIdx.x; e < (long long)mpp * mpp; e += blockDim.x) {
+        const int j = (int)(e / mpp), i = (int)(e % mpp);
+        double v = 0.0;
+        if (i >= j) {
+            if (j < m) {
+                v = (i < m) ? c.LA[(size_t)j * m + i] : c.G[(size_t)(i - m) * m + j];
+            } else {
+                double s = (i == j) ? 1.0 : 0.0;
+                for (int k = 0; k < m; ++k) s -= c.G[(size_t)(i - m) * m + k] * c.G[(size_t)(j - m) * m + k];
+                v = s;
+            }
+        }
+        c.L[(size_t)j * cap + i] = v;
+    }
+    __syncthreads();
+    chol_inplace(c.L + (size_t)m * cap + m, q, cap, &c.sd->chol_fail);
+    // publish nb_fix / chol_fail
+    __syncthreads();
+    const int nwords = sizeof(Scal) / 8;
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(c.sd);
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(c.sh);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) d[i] = s[i];
+}
+
+// projection! (:158-170): y = L \ (A~ r); w = L' \ y; v = r - A~' w   (r optionally negated first)
+__global__ void k_project(DenseCtx c, const double* r, double* v, int negate) {
+    const int m = c.m, cap = c.cap;
+    const int q = *c.q_dev;
+    const int mpp = m + q;
+    const double sgn = negate ? -1.0 : 1.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* y = c.ywork;
+    // left_mul :86-98
+    for (int i = warp; i < m; i += nw) {
+        double s = 0.0;
+        for (int j = lane; j < c.n; j += 32) s = fma(c.A[(size_t)i * c.ld + j], sgn * r[j], s);
+        s = warp_sum(s);
+        if (lane == 0) y[i] = s;
+    }
+    for (int k = threadIdx.x; k < q; k += blockDim.x) y[m + k] = sgn * r[c.fixidx[k]];
+    __syncthreads();
+    // forward substitution  L y' = y  (column-oriented)
+    for (int k = 0; k < mpp; ++k) {
+        const double yk = y[k] / c.L[(size_t)k * cap + k];
+        __syncthreads();
+        if (threadIdx.x == 0) y[k] = yk;
+        for (int i = k + 1 + threadIdx.x; i < mpp; i += blockDim.x) y[i] -= c.L[(size_t)k * cap + i] * yk;
+        __syncthreads();
+    }
+    // backward substitution  L' w = y  (row-oriented on L: w_k = (y_k - sum_{i>k} L[i][k] w_i) / L[k][k])
+    __shared__ double shd[32];
+    for (int k = mpp - 1; k >= 0; --k) {
+        double s = 0.0;
+        for (int i = k + 1 + threadIdx.x; i < mpp; i += blockDim.x) s = fma(c.L[(size_t)k * cap + i], y[i], s);
+        s = block_sum(s, shd);
+        if (threadIdx.x == 0) y[k] = (y[k] - s) / c.L[(size_t)k * cap + k];
+        __syncthreads();
+    }
+    // left_mul_tr :72-84 and v = r - A~' w
+    for (int j = threadIdx.x; j < c.n; j += blockDim.x) {
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) s = fma(c.A[(size_t)i * c.ld + j], y[i], s);
+        v[j] = s;  // temporarily A' w
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < q; k += blockDim.x) v[c.fixidx[k]] += y[m + k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < c.n; j += blockDim.x) v[j] = sgn * r[j] - v[j];
+}
+
+}  // namespace
+
+void dk_chol_aat(const DenseCtx& c, cudaStream_t st) { k_chol_aat<<<1, kDT, 0, st>>>(c); }
+void dk_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st) { k_rebuild<<<1, kDT, 0, st>>>(c, fix); }
+void dk_project(const DenseCtx& c, const double* r, double* v, bool negate, cudaStream_t st) {
+    k_project<<<1, kDT, 0, st>>>(c, r, v, negate ? 1 : 0);
+}
+
+}  // namespace bnl

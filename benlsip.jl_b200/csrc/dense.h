@@ -1,0 +1,28 @@
+// dense.h -- small dense factor / solve kernels for the general projection (m_lin > 0):
+// cholesky_aug_aat, update_chol!, left_mul, left_mul_tr, projection_nullspace!/projection_subspace!
+// (src/polyhedral_constraints.jl:35-136).  Single-CTA kernels: the systems are (m_lin + q)^2, replicated.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace bnl {
+
+struct DenseCtx {
+    int n, ld, m;          // m = m_lin
+    int cap;               // leading dimension / capacity of L (>= n)
+    const double* A;       // m x ld row-major (zero padded)
+    double* LA;            // m x m   column-major lower factor of A A'
+    double* L;             // cap x cap column-major lower factor of A~ A~'  (dim m+q)
+    double* G;             // m x cap column-major:  L_A \ A[:,fix]
+    double* ywork;         // cap
+    long long* fixidx;     // ascending indices of fixed variables (cap)
+    int* q_dev;            // number of fixed variables
+    Scal* sd;
+    Scal* sh;
+};
+
+void dk_chol_aat(const DenseCtx& c, cudaStream_t st);                              // LA = cholesky(A*A').L  (basic_tralcnlss.jl:206)
+void dk_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st);     // update_chol!  :62-68
+void dk_project(const DenseCtx& c, const double* r, double* v, bool negate, cudaStream_t st);  // projection! :158-170
+
+}  // namespace bnl

@@ -1,0 +1,25 @@
+// models.h -- built-in device-side residual / Jacobian generators (K11; definitions: oracle/models.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bnl {
+
+struct ModelArgs {
+    int model_id;
+    long long M, M_total, row0;
+    int n, ld;
+    uint32_t seed;
+    double noise;
+    const double* cs;  // GLM column scale (device, length ld, zero padded)
+};
+
+// y = model(x_true) + noise  (once, at bind time)
+cudaError_t model_setup_y(const ModelArgs& a, const double* x_true, double* y, cudaStream_t st);
+// r = model(x) - y ; sumsq_out[0] = sum r_i^2 over local rows (fixed-order two-stage reduction)
+cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y, double* r, double* partial,
+                           int nblocks, double* sumsq_out, cudaStream_t st);
+// J (row-major M x ld, zero padded) = d model / d x at x
+cudaError_t model_jacobian(const ModelArgs& a, const double* x, double* J, cudaStream_t st);
+
+}  // namespace bnl

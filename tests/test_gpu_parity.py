@@ -1,0 +1,358 @@
+"""
+GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the oracle
+(oracle/benlsip_oracle.py) on the same seeded inputs.  Floating point: FP64, tolerances written at each assert
+(north_star: final iterate / objective within 1e-10 relative, active-set words bit-exact, iteration counts equal).
+"""
+import numpy as np
+import pytest
+
+import benlsip_b200 as B
+from oracle import benlsip_oracle as O
+from oracle.models import ExpSumProblem, GlmProblem, SphereRegression
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture()
+def S():
+    s = B.Solver(0)
+    yield s
+    s.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K1-K4: the streaming Jacobian kernels, every tiling regime (TG/G/KCH/RB), ragged M, odd n
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,n", [(4, 3), (1, 1), (33, 5), (1000, 37), (4096, 256), (3001, 250), (2500, 1024), (777, 1000),
+                                 (700, 2048), (300, 4096), (129, 3000), (64, 16), (5000, 64), (200000, 128)])
+def test_alhessian_matvecs_match_numpy(S, M, n):
+    """test/structures.jl:1-16 generalised: H*v, vthv, J*v, J'*w against explicit NumPy (rtol 1e-12)."""
+    rng = np.random.default_rng(M * 7919 + n)
+    J = rng.standard_normal((M, n))
+    v = rng.standard_normal(n)
+    w = rng.standard_normal(M)
+    S.set_problem(M, n)
+    S.upload_jacobian(J)
+    Jv = J @ v
+    assert rel(S.hess_mul(v), J.T @ Jv) < 1e-12
+    assert abs(S.vthv(v) - Jv @ Jv) <= 1e-12 * (Jv @ Jv)
+    assert rel(S.jv(v), Jv) < 1e-12
+    assert rel(S.jtw(w), J.T @ w) < 1e-12
+
+
+def test_hess_mul_is_run_to_run_deterministic(S):
+    rng = np.random.default_rng(5)
+    J = rng.standard_normal((20000, 512))
+    v = rng.standard_normal(512)
+    S.set_problem(20000, 512)
+    S.upload_jacobian(J)
+    a = S.hess_mul(v)
+    for _ in range(3):
+        assert np.array_equal(a, S.hess_mul(v))  # fixed reduction order, no atomics
+
+
+def test_alhessian_with_nonlinear_constraint_block(S):
+    """test/structures.jl:1-16 verbatim shape: H = J'J + mu C'C, n = 5."""
+    rng = np.random.default_rng(0)
+    n = 5
+    J, Cm, mu, v = rng.random((n, n)), rng.random((n, n)), rng.random(), rng.random(n)
+    S.set_problem(n, n, p=n)
+    S.upload_jacobian(J)
+    S.upload_nlcons_jacobian(Cm)
+    S.set_mu(mu)
+    H_test = J.T @ J + mu * Cm.T @ Cm
+    assert rel(S.hess_mul(v), H_test @ v) < 1e-13
+    assert abs(S.vthv(v) - v @ (H_test @ v)) < 1e-13 * abs(v @ (H_test @ v))
+
+
+def test_gram_dmma_matches_numpy(S):
+    rng = np.random.default_rng(11)
+    for M, n in [(3000, 200), (5000, 384), (1000, 130)]:
+        J = rng.standard_normal((M, n))
+        S.set_problem(M, n)
+        S.upload_jacobian(J)
+        G, ms = S.gram()
+        ref = J.T @ J
+        assert np.max(np.abs(G - ref)) <= 1e-12 * np.max(np.abs(ref))
+        assert np.array_equal(G, G.T)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K11: device models against oracle/models.py
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,M,n,row0", [("glm", 4096, 64, 0), ("glm", 3001, 250, 0), ("glm", 1500, 1024, 70000),
+                                           ("expsum", 4096, 16, 0), ("expsum", 5000, 64, 123)])
+def test_builtin_models_match_oracle(S, kind, M, n, row0):
+    if kind == "glm":
+        P = GlmProblem(M, n, seed=3, row0=row0)
+        mid = B.MODEL_GLM
+        seed = 3
+        Mtot = M + row0
+    else:
+        Mtot = M + row0 + 17
+        P = ExpSumProblem(M, n, seed=1, row0=row0, M_total=Mtot)
+        mid = B.MODEL_EXPSUM
+        seed = 1
+    S.set_problem(M, n, M_total=Mtot, row0=row0)
+    S.use_builtin_model(mid, noise=1e-3, cond_exp=0.0, seed=seed)
+    mv = S.model_vectors()
+    assert np.array_equal(mv["x_true"], P.x_true)  # same hash, exact
+    assert np.array_equal(mv["xlow"], P.xlow) and np.array_equal(mv["xupp"], P.xupp) and np.array_equal(mv["x0"], P.x0)
+    x = P.x0 + 0.05 * np.cos(np.arange(n))
+    r, ss = S.residuals(x)
+    r_ref = P.residuals(x)
+    assert np.max(np.abs(r - r_ref)) <= 1e-13 * max(1.0, np.max(np.abs(r_ref)))
+    assert abs(ss - r_ref @ r_ref) <= 1e-12 * (r_ref @ r_ref)
+    S.eval_jacobian(x)
+    J = P.jac_res(x)
+    v = np.sin(np.arange(n) + 1.0)
+    assert rel(S.jv(v), J @ v) < 1e-12
+    assert rel(S.hess_mul(v), J.T @ (J @ v)) < 1e-12
+    for k in (0, n // 2, n - 1):  # individual columns of J
+        e = np.zeros(n)
+        e[k] = 1.0
+        assert np.max(np.abs(S.jv(e) - J[:, k])) <= 1e-14 * max(1.0, np.max(np.abs(J[:, k])))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K8-K10: MixedConstraints through the library (reference fixtures, test/structures.jl:18-78)
+# ---------------------------------------------------------------------------------------------------------
+def test_hs48_projection_golden_vector(S):
+    """test/structures.jl:37-58: the reference's only literal golden vector, through the CUDA path."""
+    A = np.array([[1.0, 1, 1, 1, 1], [0, 0, 1, -2, -2]])
+    x_hs = np.array([3.0, 5, -3, 2, -2])
+    S.set_problem(1, 5, A)
+    S.set_fixvars([True, True, False, False, False])
+    proj = S.projection(x_hs)
+    np.testing.assert_allclose(proj, [0.0, 0, 0, 2, -2], rtol=0, atol=1e-14)
+    v = A @ proj
+    assert np.all(np.abs(proj[:2]) <= np.finfo(float).eps) and v @ v <= np.finfo(float).eps
+    # and against the oracle on a random vector
+    cons = O.MixedConstraints(A, np.linalg.cholesky(A @ A.T), fixed=np.array([True, True, False, False, False]))
+    r = np.array([0.3, -1.2, 2.5, 0.7, -0.1])
+    np.testing.assert_allclose(S.projection(r), O.projection(cons, r), rtol=0, atol=1e-14)
+
+
+def test_block_cholesky_equals_greedy(S):
+    """test/structures.jl:18-35."""
+    rng = np.random.default_rng(1)
+    m, n = 3, 6
+    A = rng.random((m, n))
+    S.set_problem(1, n, A, -rng.random(n), rng.random(n) + 1)
+    act = [1, 3, 5]
+    fixed = np.zeros(n, dtype=bool)
+    fixed[act] = True
+    S.set_fixvars(fixed)
+    Bm = np.vstack([A, np.eye(n)[act, :]])
+    np.testing.assert_allclose(S.chol_L(), np.linalg.cholesky(Bm @ Bm.T), rtol=1e-10, atol=1e-12)
+    assert S.fixvars().tolist() == fixed.tolist()
+
+
+def test_active_bounds_identification_and_update(S):
+    """test/structures.jl:60-78."""
+    rng = np.random.default_rng(3)
+    m, n = 3, 7
+    A = rng.random((m, n))
+    S.set_problem(1, n, A, -10 * np.ones(n), 10 * np.ones(n))
+    x = rng.random(n)
+    x[1] = -10.0
+    S.active_bounds_reset(x)
+    assert S.fixvars().tolist() == [False, True, False, False, False, False, False]
+    S.add_active([2, 4])
+    S.add_active(6)
+    assert S.fixvars().tolist() == [False, True, True, False, True, False, True]
+    assert S.fixvars_words().tolist() == [0b1010110]
+    # active_bounds (polyhedral_constraints.jl:219-237) against the oracle, trust-region faces included
+    cons = O.MixedConstraints(A, np.linalg.cholesky(A @ A.T), l=-10 * np.ones(n), u=10 * np.ones(n))
+    s = np.array([0.5, 0.0, -0.5, 0.2, 0.5, -0.1, 0.3])
+    assert S.active_bounds(x, s, 0.5).tolist() == O.active_bounds(cons, x, s, 0.5).tolist()
+
+
+def test_mask_projection_is_exact_for_bound_only(S):
+    n = 70
+    S.set_problem(1, n, None, -np.ones(n), np.ones(n))
+    r = np.random.default_rng(2).standard_normal(n)
+    assert np.array_equal(S.projection(r), r)
+    S.add_active([1, 3, 64, 69])
+    v = S.projection(r)
+    fix = np.zeros(n, dtype=bool)
+    fix[[1, 3, 64, 69]] = True
+    assert np.array_equal(v[~fix], r[~fix]) and not v[fix].any()
+    assert S.fixvars_words().tolist() == [(1 << 1) | (1 << 3), (1 << 0) | (1 << 5)]
+    with pytest.raises(IndexError):
+        S.add_active(n)
+
+
+def test_error_mapping(S):
+    with pytest.raises(AssertionError):  # src/basic_tralcnlss.jl:200
+        S.set_params(eta1=0.9, eta2=0.5)
+    with pytest.raises(B.PosDefException):  # cholesky(A*A') of a rank-deficient A, :206
+        S.set_problem(1, 4, np.array([[1.0, 2, 3, 4], [2.0, 4, 6, 8]]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Step computation against the oracle: cauchy_step, projected_cg, inner_step
+# ---------------------------------------------------------------------------------------------------------
+def _glm_state(S, M, n):
+    P = GlmProblem(M, n, seed=3)
+    S.set_problem(M, n)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+    x = P.x0.copy()
+    x[::7] = 1.0  # some variables start on their upper bound
+    x[3::11] = -1.0
+    S.eval_jacobian(x)
+    J, r = P.jac_res(x), P.residuals(x)
+    g = J.T @ r
+    H = O.AlHessian(J, np.zeros((0, n)), 0.0)
+    L0 = O._cholesky_lower(np.zeros((0, 0)))
+    cons = O.MixedConstraints(P.A, L0, l=P.xlow, u=P.xupp)
+    return P, x, g, H, L0, cons
+
+
+@pytest.mark.parametrize("delta", [1e-3, 0.05, 10.0])
+def test_cauchy_step_matches_oracle(S, delta):
+    P, x, g, H, L0, cons = _glm_state(S, 3000, 96)
+    s_ref = O.cauchy_step(x, g, H, L0, cons, delta)
+    s = S.cauchy_step(x, g, delta)
+    assert rel(s, s_ref) < 1e-12
+    assert np.array_equal(S.fixvars_words(), cons.fixvars_words())
+
+
+def test_inner_step_matches_oracle(S):
+    P, x, g, H, L0, cons = _glm_state(S, 3000, 96)
+    for delta in (0.02, 0.5):
+        tr = {}
+        s_ref, pred_ref = O.inner_step(x, g, H, L0, cons, delta, 50, 0.1, 0.1, trace=tr)
+        S.reset_stats()
+        s, pred = S.inner_step(x, g, delta)
+        st = S.stats()
+        assert rel(s, s_ref) < 1e-10
+        assert abs(pred - pred_ref) <= 1e-10 * abs(pred_ref)
+        assert np.array_equal(S.fixvars_words(), cons.fixvars_words())
+        assert st["cg_iters"] == tr.get("cg_iters", 0) and st["minor_iters"] == tr.get("minor_iters", 0)
+        assert st["breakpoints"] == tr.get("breakpoints", 0)
+
+
+def test_projected_cg_matches_oracle(S):
+    P, x, g, H, L0, cons = _glm_state(S, 3000, 96)
+    O.active_bounds_reset(cons, x, L0)
+    S.active_bounds_reset(x)
+    s = np.zeros(96)
+    g_minor = g.copy()
+    n = 96
+    w_u, w_l = np.full(n, np.inf), np.full(n, -np.inf)
+    fx = cons.fixvars
+    w_u[fx] = np.minimum(cons.xupp[fx] - x[fx], 1.0)
+    w_l[fx] = np.maximum(cons.xlow[fx] - x[fx], -1.0)
+    w_ref, st_ref = O.projected_cg(g_minor, H, w_l, w_u, cons, 0.1)
+    w, st, iters = S.projected_cg(x, s, g_minor, 1.0)
+    assert st == st_ref
+    assert rel(w, w_ref) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Full solves: outer loop on the host (Python standing in for Julia), subproblems through the C ABI
+# ---------------------------------------------------------------------------------------------------------
+def _solve_both(S, P, model_id, seed, **kw):
+    tr_o, tr_g = {}, {}
+    x_o, y_o = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp,
+                            trace=tr_o, **kw)
+    S.set_problem(P.M, P.n)
+    S.use_builtin_model(model_id, 1e-3, 0.0, seed)
+    x_g, y_g = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr_g, **kw)
+    return x_o, tr_o, x_g, tr_g
+
+
+@pytest.mark.parametrize("M,n", [(4096, 64), (20000, 256), (6000, 1024)])
+def test_glm_full_solve_parity(S, M, n):
+    """cfg3 family, shrunk: same outer/inner/minor/CG counts, x within 1e-10, active-set words bit-exact."""
+    P = GlmProblem(M, n, seed=3)
+    x_o, tr_o, x_g, tr_g = _solve_both(S, P, B.MODEL_GLM, 3)
+    st = tr_g["stats"]
+    assert tr_g["outer_iters"] == tr_o["outer_iters"]
+    assert st["inner_iters"] == tr_o["inner_iters"]
+    assert st["minor_iters"] == tr_o.get("minor_iters", 0)
+    assert st["cg_iters"] == tr_o.get("cg_iters", 0)
+    assert st["breakpoints"] == tr_o.get("breakpoints", 0)
+    assert rel(x_g, x_o) < 1e-10
+    obj_g, obj_o = S.residuals(x_g, False)[1], float(np.sum(P.residuals(x_o) ** 2))
+    assert abs(obj_g - obj_o) <= 1e-10 * obj_o
+    assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+    # per-inner-iteration trace (k, mx, ||s||, delta, rho) -- the reference's log tuple (src/misc.jl:70-80)
+    for a, b in zip(tr_g["inner"], tr_o["inner"]):
+        assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"]
+        assert abs(a["mx"] - b["mx"]) <= 1e-10 * abs(b["mx"])
+        assert abs(a["delta"] - b["delta"]) <= 1e-10 * abs(b["delta"])
+
+
+def test_expsum_full_solve_parity(S):
+    """cfg2 family, shrunk.  The oracle's own sensitivity to a mere row permutation on this family is ~5e-11
+    with flickering inner counts at n = 64 (measured), so the small case is the exact-count one."""
+    P = ExpSumProblem(4096, 16, seed=1)
+    x_o, tr_o, x_g, tr_g = _solve_both(S, P, B.MODEL_EXPSUM, 1)
+    assert tr_g["outer_iters"] == tr_o["outer_iters"]
+    assert tr_g["stats"]["inner_iters"] == tr_o["inner_iters"]
+    assert rel(x_g, x_o) < 1e-9
+    assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+
+
+def test_sphere_regression_through_callbacks():
+    """cfg1: test/problems/sphere_regression.jl end to end through the library (m_lin = 1, p = 1, callbacks),
+    with the reference's three end-state assertions and trajectory parity against the oracle."""
+    P = SphereRegression
+    tr_o, tr_g = {}, {}
+    x_o, y_o = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp,
+                            max_outer_iter=100, max_inner_iter=250, trace=tr_o)
+    x_g, y_g = B.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp,
+                            max_outer_iter=100, max_inner_iter=250, trace=tr_g)
+    assert np.linalg.norm(P.nlconstraints(x_g)) < O.SQRT_EPS  # :63
+    assert O.is_feasible(x_g, P.A, P.xlow, P.xupp, P.b)  # :64
+    assert tr_g["outer_iters"] == tr_o["outer_iters"]
+    assert tr_g["stats"]["inner_iters"] == tr_o["inner_iters"]
+    assert rel(x_g, x_o) < 1e-9 and rel(y_g, y_o) < 1e-7
+    assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+
+
+def test_native_outer_loop_equals_host_outer_loop(S, tmp_path):
+    P = GlmProblem(4096, 64, seed=3)
+    S.set_problem(P.M, P.n)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+    x_h, _ = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S)
+    w_h = S.fixvars_words()
+    log = tmp_path / "benlsip.out"
+    x_n, _, mu, pix = S.tralcnllss_native(P.x0, log_path=str(log))
+    assert np.array_equal(x_h, x_n) and np.array_equal(w_h, S.fixvars_words())
+    txt = log.read_text()
+    assert "Outer iter 1" in txt and "AL value" in txt
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Full BASELINE size (cfg3: M = 1e7, n = 1024, 81.9 GB of J): size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def test_full_size_properties(S):
+    info = S.device_info()
+    M, n = 10_000_000, 1024
+    if info["free_bytes"] < 100e9:
+        M = int(info["free_bytes"] * 0.6 / (8 * n))
+    S.set_problem(M, n)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+    x0 = S.model_vectors()["x0"]
+    S.eval_jacobian(x0)
+    rng = np.random.default_rng(0)
+    v, w = rng.standard_normal(n), rng.standard_normal(n)
+    Hv, Hw = S.hess_mul(v), S.hess_mul(w)
+    # linearity, symmetry, consistency of vthv with H*v, positive semi-definiteness
+    assert rel(S.hess_mul(2.0 * v - 3.0 * w), 2.0 * Hv - 3.0 * Hw) < 1e-12
+    assert abs(v @ Hw - w @ Hv) <= 1e-12 * abs(v @ Hw)
+    q = S.vthv(v)
+    assert q > 0 and abs(q - v @ Hv) <= 1e-12 * q
+    assert np.array_equal(Hv, S.hess_mul(v))
+    # x0 = 0 => z = 0, phi'(0) = 1.1, J = 1.1 A with a_ij uniform in [-1,1)/sqrt(n): diag(J'J) ~ 1.21 M / (3 n)
+    e = np.zeros(n)
+    e[5] = 1.0
+    d = S.hess_mul(e)[5]
+    assert abs(d / (1.21 * M / (3 * n)) - 1.0) < 5e-3
