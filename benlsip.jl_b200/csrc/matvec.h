@@ -23,6 +23,7 @@ struct MvPlan {
     long long pstride;
     size_t smem_bytes;
     bool supported;
+    bool warp_team;
 };
 
 MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes);
