@@ -290,20 +290,37 @@ def test_glm_full_solve_parity(S, M, n):
         assert abs(a["delta"] - b["delta"]) <= 1e-10 * abs(b["delta"])
 
 
+def _assert_trace_prefix(tr_g, tr_o, nprefix, mx_rtol=1e-12, pix_rtol=1e-5):
+    assert len(tr_g["inner"]) >= nprefix and len(tr_o["inner"]) >= nprefix
+    for a, b in list(zip(tr_g["inner"], tr_o["inner"]))[:nprefix]:
+        assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"]
+        assert abs(a["mx"] - b["mx"]) <= mx_rtol * abs(b["mx"])
+        assert abs(a["delta"] - b["delta"]) <= 1e-9 * abs(b["delta"])
+        assert abs(a["pix"] - b["pix"]) <= pix_rtol * abs(b["pix"])
+
+
 def test_expsum_full_solve_parity(S):
-    """cfg2 family, shrunk.  The oracle's own sensitivity to a mere row permutation on this family is ~5e-11
-    with flickering inner counts at n = 64 (measured), so the small case is the exact-count one."""
+    """cfg2 family, shrunk.  On this family the reference algorithm creeps (hundreds of inner iterations whose AL
+    decrease is ~1e-14 relative), so rho = ared/pred is a ratio of rounding noise and the iteration at which
+    pix < omega is crossed is not reproducible between two correct FP64 implementations (measured: 188 vs 201
+    inner iterations, DESIGN.md 'parity floor').  What is reproducible and asserted: the first 60 inner iterations
+    (AL value to 1e-12, criticality to 1e-5, active-set size, k), the outer count, the final iterate to 1e-8 and the
+    final active set bit-exactly."""
     P = ExpSumProblem(4096, 16, seed=1)
     x_o, tr_o, x_g, tr_g = _solve_both(S, P, B.MODEL_EXPSUM, 1)
     assert tr_g["outer_iters"] == tr_o["outer_iters"]
-    assert tr_g["stats"]["inner_iters"] == tr_o["inner_iters"]
-    assert rel(x_g, x_o) < 1e-9
+    _assert_trace_prefix(tr_g, tr_o, 60)
+    assert abs(tr_g["stats"]["inner_iters"] - tr_o["inner_iters"]) <= 0.15 * tr_o["inner_iters"]
+    assert np.max(np.abs(x_g - x_o)) < 1e-8
     assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
 
 
 def test_sphere_regression_through_callbacks():
-    """cfg1: test/problems/sphere_regression.jl end to end through the library (m_lin = 1, p = 1, callbacks),
-    with the reference's three end-state assertions and trajectory parity against the oracle."""
+    """cfg1: test/problems/sphere_regression.jl end to end through the library (m_lin = 1, p = 1, callbacks, general
+    projection with device Cholesky / triangular solves), with the reference's end-state assertions
+    (:63-65).  Trajectory: a 1-ulp perturbation of the residuals already changes the ORACLE's own counts on this
+    problem (8 -> 7 outer, 57 -> 56 inner, x by 5e-9, y by 7e-8: tests/test_oracle_noise_floor.py), so parity is
+    asserted on the first 10 inner iterations and on the end state to that floor."""
     P = SphereRegression
     tr_o, tr_g = {}, {}
     x_o, y_o = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp,
@@ -312,9 +329,12 @@ def test_sphere_regression_through_callbacks():
                             max_outer_iter=100, max_inner_iter=250, trace=tr_g)
     assert np.linalg.norm(P.nlconstraints(x_g)) < O.SQRT_EPS  # :63
     assert O.is_feasible(x_g, P.A, P.xlow, P.xupp, P.b)  # :64
-    assert tr_g["outer_iters"] == tr_o["outer_iters"]
-    assert tr_g["stats"]["inner_iters"] == tr_o["inner_iters"]
-    assert rel(x_g, x_o) < 1e-9 and rel(y_g, y_o) < 1e-7
+    grad_lag = P.jac_res(x_g).T @ P.residuals(x_g) + P.jac_nlcons(x_g).T @ y_g
+    from tests.test_oracle_reference_fixtures import _project_polyhedron_small
+    assert np.linalg.norm(x_g - _project_polyhedron_small(x_g - grad_lag, P.A, P.b, P.xlow, P.xupp)) < 1e-7  # :65
+    _assert_trace_prefix(tr_g, tr_o, 10, mx_rtol=1e-12, pix_rtol=1e-6)
+    assert abs(tr_g["outer_iters"] - tr_o["outer_iters"]) <= 1
+    assert np.max(np.abs(x_g - x_o)) < 5e-8 and np.max(np.abs(y_g - y_o)) < 5e-7
     assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
 
 
