@@ -156,6 +156,8 @@ def run_ours(args, cfg):
     if world > 1:
         init_solver_comm(S)
     x0 = S.model_vectors()["x0"]
+    if args.hessian == "gram":
+        S.set_hessian_mode(B.HESSIAN_GRAM)
 
     def barrier():
         if world > 1:
@@ -196,6 +198,28 @@ def run_ours(args, cfg):
     barrier()
     t_wall = time.perf_counter() - t_begin
     sampler.stop_flag = True
+    # extra: one solve in the opt-in Gram-apply mode (G = J'J on the FP64 tensor cores once per Jacobian), reported beside
+    # the headline, never mixed into it
+    gram_extra = None
+    if args.hessian == "matrix_free" and not args.no_gram_extra:
+        S.set_hessian_mode(B.HESSIAN_GRAM)
+        step()  # warm-up (allocations)
+        barrier()
+        tg0 = time.perf_counter()
+        xg, trg, _ = step()
+        barrier()
+        tg = time.perf_counter() - tg0
+        stg = trg["stats"]
+        ldp = (n + 15) // 16 * 16
+        ntile = (ldp + 127) // 128
+        gflops = 2.0 * M_loc * (ntile * (ntile + 1) / 2) * 128 * 128
+        gram_extra = {"solve_wall_s": tg, "outer": trg["outer_iters"], "inner": stg["inner_iters"], "hess_mul": stg["hess_mul"],
+                      "j_passes": stg["j_passes"], "gram_count": stg["gram_count"],
+                      "gram_ms_avg": stg["gram_ms"] / max(stg["gram_count"], 1),
+                      "gram_tflops_per_gpu": gflops / (stg["gram_ms"] / max(stg["gram_count"], 1) * 1e-3) / 1e12 if stg["gram_ms"] > 0 else None,
+                      "x_rel_diff_vs_matrix_free": float(np.linalg.norm(xg - x) / np.linalg.norm(x)),
+                      "matvec_equiv_GBps": 8.0 * M * n * (stg["jv"] + stg["jtw"]) / tg / 1e9}
+        S.set_hessian_mode(B.HESSIAN_MATRIX_FREE)
     # max over ranks of both clocks
     if world > 1:
         tt = torch.tensor([t_wall, dev_ms], dtype=torch.float64, device="cuda")
@@ -229,6 +253,9 @@ def run_ours(args, cfg):
                              "traffic": None},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
+        line["config"]["hessian"] = args.hessian
+        if gram_extra is not None:
+            line["gram_mode"] = gram_extra
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, cfg)
         print(json.dumps(line), flush=True)
@@ -271,6 +298,9 @@ def main():
     ap.add_argument("--M", type=int, default=0, help="override the row count (debug)")
     ap.add_argument("--cpu-sample-div", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hessian", default="matrix_free", choices=["matrix_free", "gram"],
+                    help="matrix_free = the reference's J'(Jv) semantics (default, parity mode); gram = opt-in DMMA Gram-apply mode")
+    ap.add_argument("--no-gram-extra", action="store_true", help="skip the extra (untimed-in-headline) Gram-mode solve")
     args = ap.parse_args()
     cfg = CFG[args.config]
     if args.impl == "reference":

@@ -27,6 +27,7 @@ SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)
 # CG_status (src/basic_tralcnlss.jl:12); NOTHING is Julia's `nothing` (trap T3)
 CG_SOLVED, CG_BOUND_HIT, CG_NEGATIVE_CURVATURE, CG_MAX_ITER, CG_NOTHING = 0, 1, 2, 3, -1
 MODEL_GLM, MODEL_EXPSUM = 1, 2
+HESSIAN_MATRIX_FREE, HESSIAN_GRAM = 0, 1
 
 
 class BnlError(RuntimeError):
@@ -66,7 +67,7 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("outer_iters", "inner_iters", "minor_iters", "cg_iters", "breakpoints", "hess_mul",
                                           "vthv", "jtw", "jv", "res_eval", "jac_eval", "chol_rebuilds", "allreduces")] + \
                [(k, C.c_double) for k in ("hess_mul_ms", "vthv_ms", "jtw_ms", "res_eval_ms", "jac_eval_ms", "solve_ms")] + \
-               [("kernel_launches", C.c_int64)]
+               [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -113,7 +114,7 @@ def load_library(build_if_missing: bool = False):
         "bnl_set_mu": ([H, dbl], C.c_int), "bnl_eval_jacobian": ([H, _DP], C.c_int),
         "bnl_residuals": ([H, _DP, _DP, _DP], C.c_int), "bnl_hess_mul": ([H, _DP, _DP], C.c_int),
         "bnl_vthv": ([H, _DP, _DP], C.c_int), "bnl_jv": ([H, _DP, _DP], C.c_int), "bnl_jtw": ([H, _DP, _DP], C.c_int),
-        "bnl_gram": ([H, _DP, _DP], C.c_int), "bnl_project": ([H, _DP, _DP], C.c_int),
+        "bnl_gram": ([H, _DP, _DP], C.c_int), "bnl_set_hessian_mode": ([H, i32], C.c_int), "bnl_project": ([H, _DP, _DP], C.c_int),
         "bnl_active_bounds_reset": ([H, _DP], C.c_int),
         "bnl_active_bounds": ([H, _DP, _DP, dbl, C.POINTER(i64), C.POINTER(i32)], C.c_int),
         "bnl_add_active": ([H, C.POINTER(i64), i32], C.c_int),
@@ -313,6 +314,10 @@ class Solver:
         ms = C.c_double()
         self._ck(self.lib.bnl_gram(self.h, _p(G), C.byref(ms)))
         return G, ms.value
+
+    def set_hessian_mode(self, mode):
+        """HESSIAN_MATRIX_FREE (reference semantics, default) or HESSIAN_GRAM (G = J'J on the FP64 tensor cores)."""
+        self._ck(self.lib.bnl_set_hessian_mode(self.h, int(mode)))
 
     # -- MixedConstraints -----------------------------------------------------------------------------------
     def projection(self, r):

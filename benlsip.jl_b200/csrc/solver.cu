@@ -89,7 +89,11 @@ struct bnl_solver {
     int* d_count = nullptr;
     Scal *sd = nullptr, *sh = nullptr;
     MvPlan plan{};
-    double* gram = nullptr;
+    double* gram = nullptr;     // G = J'J (ld x ld), all-reduced
+    double* gram_ws = nullptr;  // split-K workspace
+    int gram_nsplit = 0;
+    int hess_mode = 0;          // BNL_HESSIAN_MATRIX_FREE / BNL_HESSIAN_GRAM
+    bool gram_valid = false;
 
     // model binding
     int model_id = 0;
@@ -158,6 +162,7 @@ int sync(S* h) {
                 case 2: h->st.jtw_ms += ms; break;
                 case 3: h->st.res_eval_ms += ms; break;
                 case 4: h->st.jac_eval_ms += ms; break;
+                case 5: h->st.gram_ms += ms; break;
             }
             h->ev_free.push_back(e);
             h->ev_busy[i] = h->ev_busy.back();
@@ -226,16 +231,44 @@ int allreduce(S* h, double* buf, size_t count) {
     return BNL_OK;
 }
 
+// ---- Gram mode (K12): G = J'J on the FP64 tensor cores, all-reduced over the row shards ---------------------
+int form_gram(S* h) {
+    const size_t ld = h->ld;
+    if (!h->gram) {
+        h->gram_nsplit = gram_pick_split(h->M, h->ld, h->prop.multiProcessorCount);
+        CK(cudaMalloc(&h->gram, ld * ld * sizeof(double)));
+        CK(cudaMalloc(&h->gram_ws, (size_t)h->gram_nsplit * ld * ld * sizeof(double)));
+    }
+    {
+        EvScope ev(h, 5);
+        CK(gram_launch(h->J, h->M, h->ld, h->gram, h->gram_ws, h->gram_nsplit, h->stream));
+    }
+    h->st.kernel_launches += 2;
+    h->st.j_passes += 1;  // every J element is staged once per 128-column tile pair from L2; HBM sees ~1 pass per tile row
+    RET(allreduce(h, h->gram, ld * ld));
+    h->st.gram_count++;
+    h->gram_valid = true;
+    return BNL_OK;
+}
+
 // ---- AlHessian -------------------------------------------------------------------------------------------
 // Base.:*(H,v) :102-106.  dv: device, length ld.  out: device, length >= ld+1 (out[ld] = ||Jv||^2, global).
 int hess_mul(S* h, const double* dv, double* out) {
     if (!h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound (bnl_eval_jacobian / bnl_upload_jacobian first)");
-    {
+    if (h->hess_mode == BNL_HESSIAN_GRAM) {
+        if (!h->gram_valid) RET(form_gram(h));
         EvScope ev(h, 0);
-        CK(mv_launch(MODE_JTJV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, out, h->stream));
+        CK(gram_apply(h->gram, h->n, h->ld, dv, out, h->stream));
+        h->st.kernel_launches += 2;
+    } else {
+        {
+            EvScope ev(h, 0);
+            CK(mv_launch(MODE_JTJV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, out, h->stream));
+        }
+        h->st.kernel_launches += 2;
+        h->st.j_passes += 1;
+        RET(allreduce(h, out, (size_t)h->ld + 1));
     }
-    h->st.kernel_launches += 2;
-    RET(allreduce(h, out, (size_t)h->ld + 1));
     if (h->p > 0) {
         vk_hess_c(h->vc, dv, out, true, h->stream);
         KLAUNCH();
@@ -249,12 +282,21 @@ int hess_mul(S* h, const double* dv, double* out) {
 // vthv(H,v) :92-96 -> leaves ||Jv||^2 in vc.hv[ld] (global) and Cv_sumsq in the scalars
 int vthv_dev(S* h, const double* dv) {
     if (!h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
-    {
+    if (h->hess_mode == BNL_HESSIAN_GRAM) {
+        if (!h->gram_valid) RET(form_gram(h));
         EvScope ev(h, 1);
-        CK(mv_launch(MODE_JV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, h->vc.hv, h->stream));
+        CK(gram_apply(h->gram, h->n, h->ld, dv, h->vc.t1, h->stream));  // t1[ld] = v'Gv
+        CK(cudaMemcpyAsync(h->vc.hv + h->ld, h->vc.t1 + h->ld, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        h->st.kernel_launches += 2;
+    } else {
+        {
+            EvScope ev(h, 1);
+            CK(mv_launch(MODE_JV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, h->vc.hv, h->stream));
+        }
+        h->st.kernel_launches += 2;
+        h->st.j_passes += 1;
+        RET(allreduce(h, h->vc.hv + h->ld, 1));
     }
-    h->st.kernel_launches += 2;
-    RET(allreduce(h, h->vc.hv + h->ld, 1));
     if (h->p > 0) {
         vk_hess_c(h->vc, dv, nullptr, false, h->stream);
         KLAUNCH();
@@ -272,6 +314,7 @@ int jtw_dev(S* h, const double* dw, double* out) {
         CK(mv_launch(MODE_JTW, h->plan, h->J, h->M, nullptr, dw, nullptr, h->partial, out, h->stream));
     }
     h->st.kernel_launches += 2;
+    h->st.j_passes += 1;
     RET(allreduce(h, out, (size_t)h->ld));
     h->st.jtw++;
     return BNL_OK;
@@ -390,7 +433,9 @@ int eval_jacobian(S* h, const double* dx) {
         }
     }
     h->have_J = true;
+    h->gram_valid = false;
     h->st.jac_eval++;
+    if (h->hess_mode == BNL_HESSIAN_GRAM) RET(form_gram(h));
     return BNL_OK;
 }
 
@@ -686,6 +731,9 @@ int free_problem(S* h) {
     cudaFree(h->d_cs);
     cudaFree(h->d_xtrue);
     cudaFree(h->gram);
+    cudaFree(h->gram_ws);
+    h->gram_ws = nullptr;
+    h->gram_valid = false;
     cudaFree(h->vc.C);
     cudaFree((void*)h->dc.A);
     cudaFree(h->dc.LA);
@@ -1060,6 +1108,7 @@ int bnl_upload_jacobian(bnl_handle h, const double* J_colmajor, int64_t ldj) {
     if (!J_colmajor || ldj < h->M) return h->fail(BNL_EDIM, "DimensionMismatch: ldj < M");
     RET(upload_colmajor(h, J_colmajor, h->M, h->n, ldj, h->J, h->ld));
     h->have_J = true;
+    h->gram_valid = false;
     return BNL_OK;
 }
 
@@ -1151,27 +1200,22 @@ int bnl_gram(bnl_handle h, double* G_colmajor, double* ms) {
     ENTER();
     if (!h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
     const size_t ld = h->ld;
-    const int nsplit = gram_pick_split(h->M, h->ld, h->prop.multiProcessorCount);
-    if (!h->gram) CK(cudaMalloc(&h->gram, (size_t)(nsplit + 1) * ld * ld * sizeof(double)));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, h->stream));
-    CK(gram_launch(h->J, h->M, h->ld, h->gram, h->gram + ld * ld, nsplit, h->stream));
-    CK(cudaEventRecord(e1, h->stream));
-    RET(allreduce(h, h->gram, ld * ld));
+    const double before = h->st.gram_ms;
+    RET(form_gram(h));
     RET(sync(h));
-    float t = 0.f;
-    cudaEventElapsedTime(&t, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (ms) *ms = t;
+    if (ms) *ms = h->st.gram_ms - before;
     if (G_colmajor) {
         std::vector<double> tmp(ld * ld);
         RET(get_vec(h, h->gram, tmp.data(), ld * ld));
         for (int j = 0; j < h->n; ++j)
             for (int i = 0; i < h->n; ++i) G_colmajor[(size_t)j * h->n + i] = tmp[(size_t)i * ld + j];
     }
+    return BNL_OK;
+}
+
+int bnl_set_hessian_mode(bnl_handle h, int32_t mode) {
+    if (!valid(h) || (mode != BNL_HESSIAN_MATRIX_FREE && mode != BNL_HESSIAN_GRAM)) return BNL_EINVAL;
+    h->hess_mode = mode;
     return BNL_OK;
 }
 
@@ -1410,7 +1454,8 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
     ENTER();
     if (reps < 1) return BNL_EINVAL;
     if (kind <= 2 && !h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
-    if (kind >= 3 && h->model_id == 0) return h->fail(BNL_EINVAL, "builtin model needed");
+    if ((kind == 3 || kind == 4) && h->model_id == 0) return h->fail(BNL_EINVAL, "builtin model needed");
+    if (kind == 5 && !h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
     const double Jbytes = 8.0 * (double)h->M * (double)h->ld;
     double bytes = 0.0;
     cudaEvent_t e0, e1;
@@ -1440,6 +1485,11 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
             case 4:
                 CK(model_jacobian(margs(h), h->vc.x, h->J, h->stream));
                 bytes = Jbytes;
+                break;
+            case 5:
+                if (!h->gram) RET(form_gram(h));
+                CK(gram_launch(h->J, h->M, h->ld, h->gram, h->gram_ws, h->gram_nsplit, h->stream));
+                bytes = gram_flops(h->M, h->ld);  // FLOPs, not bytes, for this kind
                 break;
             default: return h->fail(BNL_EINVAL, "kind");
         }

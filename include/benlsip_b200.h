@@ -78,6 +78,9 @@ typedef struct bnl_stats {
     double vthv_ms, jtw_ms, res_eval_ms, jac_eval_ms;
     double solve_ms;      /* CUDA-event duration of the last bnl_solve_subproblem / bnl_tralcnllss      */
     int64_t kernel_launches;
+    int64_t j_passes;     /* streaming passes over the Jacobian actually executed                     */
+    int64_t gram_count;   /* Gram formations (BNL_HESSIAN_GRAM)                                        */
+    double gram_ms;
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */
@@ -85,6 +88,11 @@ typedef struct bnl_inner_record {
     int32_t k, nb_fix;
     double mx, norm_s, delta, rho, pix, pred;
 } bnl_inner_record;
+
+/* How Base.:*(H,v) / vthv are evaluated.  MATRIX_FREE (default) is the reference's J'(Jv) (src/basic_tralcnlss.jl:102-106),
+ * fused into one HBM pass.  GRAM forms G = J'J once per Jacobian on the FP64 tensor cores (DMMA) and applies H from G:
+ * same mathematics, different rounding (kappa(G) = kappa(J)^2) => opt-in, validated separately.        */
+enum { BNL_HESSIAN_MATRIX_FREE = 0, BNL_HESSIAN_GRAM = 1 };
 
 /* Built-in device-side models (definitions in oracle/models.py, the executable spec). */
 enum { BNL_MODEL_GLM = 1, BNL_MODEL_EXPSUM = 2 };
@@ -133,7 +141,8 @@ int bnl_hess_mul(bnl_handle h, const double* v, double* Hv);     /* Base.:*(H,v)
 int bnl_vthv(bnl_handle h, const double* v, double* out);        /* vthv(H,v)      :92-96   */
 int bnl_jv(bnl_handle h, const double* v, double* Jv_local);     /* H.J*v          :93,:103 */
 int bnl_jtw(bnl_handle h, const double* w_local, double* JTw);   /* H.J'*w         :105,:45 */
-int bnl_gram(bnl_handle h, double* G_colmajor /*n x n or NULL*/, double* ms); /* J'J (+mu C'C): K12, not in the reference */
+int bnl_gram(bnl_handle h, double* G_colmajor /*n x n or NULL*/, double* ms); /* J'J: K12, not in the reference */
+int bnl_set_hessian_mode(bnl_handle h, int32_t mode);
 
 /* ---- MixedConstraints methods (src/polyhedral_constraints.jl) --------------------------------------- */
 int bnl_project(bnl_handle h, const double* r, double* v);                 /* projection!          :158-170 */
@@ -170,7 +179,8 @@ int bnl_reset_stats(bnl_handle h);
 int bnl_get_inner_log(bnl_handle h, bnl_inner_record* out, int32_t capacity, int32_t* count);
 /* Device-side microbenchmarks for the roofline report: `reps` back-to-back launches of one kernel class
  * timed with CUDA events on the library's stream; kind: 0 fused J'(Jv), 1 Jv (norm only), 2 J'w,
- * 3 residual eval, 4 Jacobian generation.  Returns average ms per launch and algorithmic bytes per launch. */
+ * 3 residual eval, 4 Jacobian generation, 5 Gram (DMMA; FLOPs are returned in bytes_per_launch).
+ * Returns average ms per launch and algorithmic bytes per launch. */
 int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, double* bytes_per_launch);
 int bnl_device_info(bnl_handle h, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* free_bytes,
                     int64_t* total_bytes);

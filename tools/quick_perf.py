@@ -24,5 +24,7 @@ for M, n in cases:
     for kind, name in [(0, "jtjv"), (1, "jv"), (2, "jtw"), (3, "residual"), (4, "jacobian")]:
         ms, nbytes = S.time_kernel(kind, 20)
         out[name] = {"ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1)}
+    ms, fl = S.time_kernel(5, 3)
+    out["gram"] = {"ms": round(ms, 3), "TFLOPs_issued": round(fl / ms / 1e9, 2), "TFLOPs_2Mn2": round(2.0 * M * n * n / ms / 1e9, 2)}
     print(json.dumps(out), flush=True)
 S.close()
