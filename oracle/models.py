@@ -236,3 +236,49 @@ class SphereRegression:
     @staticmethod
     def jac_nlcons(x):
         return np.array([[2 * x[0], 2 * x[1], 2 * x[2]]])
+
+
+# --------------------------------------------------------------------------------------
+class MixedConstraintProblem:
+    """
+    cfg4 family, host-callback form (shrunk): GLM residual r_i = phi(a_i.x) - y_i with
+      * m_lin linear equalities A x = b (A from the hash, b = A x_feas, x0 = x_feas strictly inside the box),
+      * p = 1 nonlinear equality  ||x||^2 = ||x_star||^2  (sphere through a box-feasible point),
+      * box [-1, 1]^n.
+    Exercises the general projection (Cholesky of A~A~', triangular solves), the AL multiplier / penalty updates and
+    the C-block of the GN Hessian.  Dense NumPy callbacks (the reference's calling convention).
+    """
+
+    def __init__(self, M, n, m_lin, seed=5, noise=1e-3):
+        self.M, self.n, self.m_lin, self.seed = int(M), int(n), int(m_lin), int(seed)
+        i = np.arange(M, dtype=np.uint64)
+        j = np.arange(n)
+        self.Ad = sym(seed, i, j) / np.sqrt(float(n))
+        self.A = sym(seed + 7, np.arange(m_lin, dtype=np.uint64), j)
+        z0 = np.zeros(1, dtype=np.uint64)
+        self.x_star = 0.6 * sym(seed + 2, z0, j)[0]
+        x_feas = 0.3 * sym(seed + 3, z0, j)[0]
+        # put x_star on the affine set through x_feas:  x_star <- x_star - A^+ A (x_star - x_feas)
+        AAt = self.A @ self.A.T
+        self.x_star = self.x_star - self.A.T @ np.linalg.solve(AAt, self.A @ (self.x_star - x_feas))
+        self.b = self.A @ x_feas
+        self.x0 = x_feas
+        self.rho2 = float(self.x_star @ self.x_star)
+        self.xlow = -np.ones(n)
+        self.xupp = np.ones(n)
+        zt = self.Ad @ self.x_star
+        self.y = zt + 0.1 * np.sin(zt) + noise * sym(seed + 1, i, z0)[:, 0]
+
+    def residuals(self, x):
+        z = self.Ad @ x
+        return z + 0.1 * np.sin(z) - self.y
+
+    def jac_res(self, x):
+        z = self.Ad @ x
+        return (1.0 + 0.1 * np.cos(z))[:, None] * self.Ad
+
+    def nlconstraints(self, x):
+        return np.array([x @ x - self.rho2])
+
+    def jac_nlcons(self, x):
+        return (2.0 * x)[None, :]

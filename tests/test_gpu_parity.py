@@ -8,7 +8,7 @@ import pytest
 
 import benlsip_b200 as B
 from oracle import benlsip_oracle as O
-from oracle.models import ExpSumProblem, GlmProblem, SphereRegression
+from oracle.models import ExpSumProblem, GlmProblem, MixedConstraintProblem, SphereRegression
 
 pytestmark = pytest.mark.gpu
 
@@ -338,6 +338,57 @@ def test_sphere_regression_through_callbacks():
     assert abs(tr_g["outer_iters"] - tr_o["outer_iters"]) <= 1
     assert np.max(np.abs(x_g - x_o)) < 5e-8 and np.max(np.abs(y_g - y_o)) < 5e-7
     assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+
+
+def test_cfg4_family_mixed_constraints_full_solve_parity():
+    """cfg4 family (shrunk, host callbacks): m_lin = 4 linear equalities + 1 nonlinear sphere constraint + box, the AL
+    loop really exercised (mu goes 10 -> 1e9).  General projection on the device (Cholesky of A~A~', rebuilt on every
+    add_active!, triangular solves).  The oracle is insensitive to 1-ulp perturbations on this problem (same counts,
+    dx 9e-16), so counts are asserted exactly."""
+    P = MixedConstraintProblem(600, 24, 4)
+    kw = dict(max_outer_iter=60, max_inner_iter=200)
+    tr_o, tr_g = {}, {}
+    x_o, y_o = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr_o, **kw)
+    x_g, y_g = B.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr_g, **kw)
+    st = tr_g["stats"]
+    assert tr_g["mu"] == tr_o["mu"] and tr_o["mu"] > 10.0
+    assert (tr_g["outer_iters"], st["inner_iters"], st["minor_iters"], st["cg_iters"], st["breakpoints"]) == \
+           (tr_o["outer_iters"], tr_o["inner_iters"], tr_o.get("minor_iters", 0), tr_o.get("cg_iters", 0), tr_o.get("breakpoints", 0))
+    assert rel(x_g, x_o) < 1e-10 and rel(y_g, y_o) < 1e-8
+    assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+    assert abs(P.nlconstraints(x_g)[0]) < 1e-8 and np.max(np.abs(P.A @ x_g - P.b)) < 1e-12
+    assert st["chol_rebuilds"] > 0
+
+
+def test_cfg5_family_ill_conditioned_inner_steps(S):
+    """cfg5 family (column scaling 10^(-6 j/n), kappa(J'J) ~ 1e12), shrunk.  The reference algorithm does not reach its
+    tolerance on this family in any reasonable number of iterations (oracle: 20 outer x 100 inner x ~50 CG at n = 64), so
+    parity is asserted per inner step: Cauchy point, CG iterates, predicted reduction, active set."""
+    M, n = 3000, 96
+    P = GlmProblem(M, n, seed=3, cond_exp=6.0)
+    S.set_problem(M, n)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 6.0, 3)
+    assert np.allclose(S.model_vectors()["x_true"], P.x_true)
+    x = P.x0.copy()
+    L0 = O._cholesky_lower(np.zeros((0, 0)))
+    cons = O.MixedConstraints(P.A, L0, l=P.xlow, u=P.xupp)
+    for it in range(3):
+        S.eval_jacobian(x)
+        J, r = P.jac_res(x), P.residuals(x)
+        g = J.T @ r
+        assert rel(S.jtw(S.residuals(x)[0]), g) < 1e-11
+        H = O.AlHessian(J, np.zeros((0, n)), 0.0)
+        delta = 0.1 * np.linalg.norm(g)
+        tr = {}
+        s_ref, pred_ref = O.inner_step(x, g, H, L0, cons, delta, 50, 0.1, 0.1, trace=tr)
+        S.reset_stats()
+        s, pred = S.inner_step(x, g, delta)
+        st = S.stats()
+        assert st["cg_iters"] == tr.get("cg_iters", 0) and st["breakpoints"] == tr.get("breakpoints", 0)
+        assert rel(s, s_ref) < 1e-7  # CG on kappa ~ 1e12 amplifies rounding; the step still agrees to 7 digits
+        assert abs(pred - pred_ref) <= 1e-8 * abs(pred_ref)
+        assert np.array_equal(S.fixvars_words(), cons.fixvars_words())
+        x = x + s_ref
 
 
 @pytest.mark.parametrize("M,n", [(4096, 64), (20000, 256)])
