@@ -254,6 +254,11 @@ def run_ours(args, cfg):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
         line["config"]["hessian"] = args.hessian
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if world == 1 and M == CFG["cfg3"]["M"] and n == 1024 and args.hessian == "matrix_free" and os.path.exists(tp):
+            tj = json.load(open(tp))  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+            line["roofline"]["traffic"] = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+            line["roofline"]["traffic_source"] = tj["source"]
         if gram_extra is not None:
             line["gram_mode"] = gram_extra
         if world == 1 and not args.no_cpu_baseline:
