@@ -237,14 +237,15 @@ def run_ours(args, cfg):
                 "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.config, "M": M, "n": n, "model": cfg["model"], "rows_per_gpu": M_loc,
-                           "parallelism": f"row-sharded x{world}", "l2": "J shard (>= 10 GB) far exceeds the 126 MB L2",
+                           "parallelism": f"row-sharded x{world}", "collective": ("fused NVLink peer-memory all-reduce" if S.comm_info()["p2p_allreduce"] else ("nccl" if world > 1 else "none")), "l2": "J shard (>= 10 GB) far exceeds the 126 MB L2",
                            "bytes_accounting": "8*M*n per J.v or J'.w product; a fused Hessian apply = 2 products, 1 HBM pass",
                            "step": "one full tralcnllss solve to the reference tolerances (defaults)"},
                 "solve_wall_s": t_wall / args.steps, "solve_device_s": dev_ms * 1e-3 / args.steps,
                 "counts": {"outer": tr["outer_iters"], "inner": tr["stats"]["inner_iters"], "minor": tr["stats"]["minor_iters"],
                            "cg": tr["stats"]["cg_iters"], "breakpoints": tr["stats"]["breakpoints"], "hess_mul": tr["stats"]["hess_mul"],
                            "vthv": tr["stats"]["vthv"], "jtw": tr["stats"]["jtw"], "jac_eval": tr["stats"]["jac_eval"],
-                           "res_eval": tr["stats"]["res_eval"], "allreduces": tr["stats"]["allreduces"]},
+                           "res_eval": tr["stats"]["res_eval"], "allreduces": tr["stats"]["allreduces"],
+                           "p2p_allreduces": tr["stats"]["p2p_allreduces"]},
                 "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"])),
                           "x_err_inf_vs_true_interior": None},
                 "roofline": {"bound": "hbm", "kernel": "mv_stream_kernel<JTJV> (fused J'(Jv), one pass)", "achieved": achieved,

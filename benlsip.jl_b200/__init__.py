@@ -67,7 +67,8 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("outer_iters", "inner_iters", "minor_iters", "cg_iters", "breakpoints", "hess_mul",
                                           "vthv", "jtw", "jv", "res_eval", "jac_eval", "chol_rebuilds", "allreduces")] + \
                [(k, C.c_double) for k in ("hess_mul_ms", "vthv_ms", "jtw_ms", "res_eval_ms", "jac_eval_ms", "solve_ms")] + \
-               [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double)]
+               [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double),
+                ("p2p_allreduces", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -106,6 +107,7 @@ def load_library(build_if_missing: bool = False):
         "bnl_default_params": ([C.POINTER(Params)], None), "bnl_default_outer_params": ([C.POINTER(OuterParams)], None),
         "bnl_set_params": ([H, C.POINTER(Params)], C.c_int),
         "bnl_comm_unique_id": ([C.c_void_p], C.c_int), "bnl_comm_init": ([H, C.c_int, C.c_int, C.c_void_p], C.c_int),
+        "bnl_comm_info": ([H, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
         "bnl_set_problem": ([H, i64, i64, i64, i32, i32, i32, _DP, _DP, _DP], C.c_int),
         "bnl_use_builtin_model": ([H, i32, _DP, i32, C.c_uint32], C.c_int),
         "bnl_use_callbacks": ([H, CALLBACK, CALLBACK, CALLBACK, CALLBACK, C.c_void_p], C.c_int),
@@ -204,6 +206,11 @@ class Solver:
     def comm_init(self, nranks: int, rank: int, unique_id: bytes | None):
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         self._ck(self.lib.bnl_comm_init(self.h, nranks, rank, buf))
+
+    def comm_info(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.bnl_comm_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(nranks=a.value, rank=b.value, p2p_allreduce=bool(c.value))
 
     @staticmethod
     def comm_unique_id() -> bytes:

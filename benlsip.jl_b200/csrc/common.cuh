@@ -37,7 +37,7 @@ struct Scal {
     double cdot_yc, cdot_cc;   // dot(y,cx), dot(cx,cx)
     double Cv_sumsq;           // dot(Cv,Cv)
     int chol_fail;             // device Cholesky hit a non-positive pivot
-    int pad_;
+    int p2p_timeout;           // peer-memory all-reduce gave up waiting for a rank
 };
 
 // ---- block-wide deterministic reductions (fixed tree => run-to-run bit-identical) --------------------

@@ -24,6 +24,7 @@
 // Algorithmic bytes per launch (what roofline.achieved uses): 8*M_loc*ld (+ O(n)); J is read exactly once.
 #include "common.cuh"
 #include "matvec.h"
+#include "p2p.h"
 
 namespace bnl {
 
@@ -360,6 +361,30 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
     out[j] = s;
 }
 
+// reduce_partials_kernel + the push half of the peer-memory all-reduce in ONE kernel: the column sums of this rank
+// go straight into every peer's mailbox over NVLink (p2p.h); out is not written here (p2p_wait_sum does it).
+__global__ void reduce_push_kernel(const double* __restrict__ partial, int nparts, long long pstride, int col0, int ncols,
+                                   P2PArgs p2p, unsigned long long epoch) {
+    const int j = col0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ncols) {
+        double s = 0.0;
+        int c = 0;
+        for (; c + 4 <= nparts; c += 4) {
+            const double a0 = partial[(size_t)(c + 0) * pstride + j];
+            const double a1 = partial[(size_t)(c + 1) * pstride + j];
+            const double a2 = partial[(size_t)(c + 2) * pstride + j];
+            const double a3 = partial[(size_t)(c + 3) * pstride + j];
+            s += a0;
+            s += a1;
+            s += a2;
+            s += a3;
+        }
+        for (; c < nparts; ++c) s += partial[(size_t)c * pstride + j];
+        p2p_push_value(p2p, epoch, j, s);
+    }
+    p2p_push_finish(p2p, epoch);
+}
+
 }  // namespace
 
 // ---- host-side planning ---------------------------------------------------------------------------------
@@ -410,7 +435,8 @@ MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes) {
 }
 
 cudaError_t mv_launch(int mode, const MvPlan& p, const double* J, long long M, const double* v, const double* w,
-                      double* t_out, double* partial, double* out, cudaStream_t stream) {
+                      double* t_out, double* partial, double* out, cudaStream_t stream, const P2PArgs* p2p,
+                      unsigned long long epoch) {
     if (!p.supported) return cudaErrorInvalidValue;
     MvArgs a{};
     a.J = J;
@@ -434,6 +460,13 @@ cudaError_t mv_launch(int mode, const MvPlan& p, const double* J, long long M, c
     if (e != cudaSuccess) return e;
     const int ncols = p.ld + 1;
     const int col0 = (mode == MODE_JV) ? p.ld : 0;  // JV only produces the sum-of-squares slot
+    if (p2p != nullptr) {
+        // fused local reduce + NVLink push; then wait for all ranks and sum in rank order (bit-identical everywhere)
+        reduce_push_kernel<<<(ncols - col0 + 127) / 128, 128, 0, stream>>>(partial, p.grid, p.pstride, col0, ncols, *p2p, epoch);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return p2p_wait_sum(*p2p, epoch, out, col0, ncols, stream);
+    }
     reduce_partials_kernel<<<(ncols - col0 + 127) / 128, 128, 0, stream>>>(partial, p.grid, p.pstride, col0, ncols, out);
     return cudaGetLastError();
 }

@@ -30,7 +30,10 @@ MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes);
 
 // Launches the streaming kernel + the fixed-order partial reduction on `stream`.
 // out: length ld+1 doubles; out[0..ld) = J'(Jv) or J'w, out[ld] = sum (Jv)_i^2 (JTJV, JV modes).
+// p2p != nullptr: the partial reduction also pushes to every peer's mailbox and `out` holds the ALL-REDUCED result.
+struct P2PArgs;
 cudaError_t mv_launch(int mode, const MvPlan& p, const double* J, long long M, const double* v, const double* w,
-                      double* t_out, double* partial, double* out, cudaStream_t stream);
+                      double* t_out, double* partial, double* out, cudaStream_t stream, const P2PArgs* p2p = nullptr,
+                      unsigned long long epoch = 0);
 
 }  // namespace bnl

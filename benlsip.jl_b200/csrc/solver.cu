@@ -23,6 +23,7 @@
 #include "gram.h"
 #include "matvec.h"
 #include "models.h"
+#include "p2p.h"
 #include "vecops.h"
 
 using namespace bnl;
@@ -36,6 +37,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (lib) return true;
@@ -49,6 +51,7 @@ struct NcclApi {
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
         return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
     }
@@ -114,6 +117,13 @@ struct bnl_solver {
     // comm
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer-memory all-reduce (p2p.h)
+    bool p2p_on = false;
+    P2PArgs p2p{};
+    double* p2p_buf = nullptr;
+    unsigned int* p2p_counter = nullptr;
+    unsigned long long p2p_epoch = 0;
+    void* p2p_opened[kP2PMaxRanks] = {nullptr};
 
     bnl_stats st{};
     std::vector<bnl_inner_record> ilog;
@@ -150,6 +160,8 @@ typedef bnl_solver S;
 
 int sync(S* h) {
     CK(cudaStreamSynchronize(h->stream));
+    // (the O(n) kernel that follows every all-reduce publishes the scalars, p2p_timeout included)
+    if (h->p2p_on && h->sh->p2p_timeout) return h->fail(BNL_ENCCL, "peer-memory all-reduce timed out waiting for a rank");
     // harvest finished event pairs
     for (size_t i = 0; i < h->ev_busy.size();) {
         EvPair& e = h->ev_busy[i];
@@ -225,6 +237,13 @@ int get_vec(S* h, const double* src_dev, double* dst, size_t count) {
 
 int allreduce(S* h, double* buf, size_t count) {
     if (h->nranks <= 1) return BNL_OK;
+    if (h->p2p_on && count <= (size_t)kP2PWidth) {
+        CK(p2p_allreduce(h->p2p, ++h->p2p_epoch, buf, (int)count, h->stream));
+        h->st.kernel_launches += 2;
+        h->st.allreduces++;
+        h->st.p2p_allreduces++;
+        return BNL_OK;
+    }
     ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess) return h->fail(BNL_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     h->st.allreduces++;
@@ -261,13 +280,20 @@ int hess_mul(S* h, const double* dv, double* out) {
         CK(gram_apply(h->gram, h->n, h->ld, dv, out, h->stream));
         h->st.kernel_launches += 2;
     } else {
+        const bool fused = h->p2p_on;  // reduce + NVLink push in one kernel, then wait+sum
         {
             EvScope ev(h, 0);
-            CK(mv_launch(MODE_JTJV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, out, h->stream));
+            CK(mv_launch(MODE_JTJV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, out, h->stream,
+                         fused ? &h->p2p : nullptr, fused ? ++h->p2p_epoch : 0));
         }
-        h->st.kernel_launches += 2;
+        h->st.kernel_launches += fused ? 3 : 2;
         h->st.j_passes += 1;
-        RET(allreduce(h, out, (size_t)h->ld + 1));
+        if (fused) {
+            h->st.allreduces++;
+            h->st.p2p_allreduces++;
+        } else {
+            RET(allreduce(h, out, (size_t)h->ld + 1));
+        }
     }
     if (h->p > 0) {
         vk_hess_c(h->vc, dv, out, true, h->stream);
@@ -289,13 +315,20 @@ int vthv_dev(S* h, const double* dv) {
         CK(cudaMemcpyAsync(h->vc.hv + h->ld, h->vc.t1 + h->ld, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         h->st.kernel_launches += 2;
     } else {
+        const bool fused = h->p2p_on;
         {
             EvScope ev(h, 1);
-            CK(mv_launch(MODE_JV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, h->vc.hv, h->stream));
+            CK(mv_launch(MODE_JV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, h->vc.hv, h->stream,
+                         fused ? &h->p2p : nullptr, fused ? ++h->p2p_epoch : 0));
         }
-        h->st.kernel_launches += 2;
+        h->st.kernel_launches += fused ? 3 : 2;
         h->st.j_passes += 1;
-        RET(allreduce(h, h->vc.hv + h->ld, 1));
+        if (fused) {
+            h->st.allreduces++;
+            h->st.p2p_allreduces++;
+        } else {
+            RET(allreduce(h, h->vc.hv + h->ld, 1));
+        }
     }
     if (h->p > 0) {
         vk_hess_c(h->vc, dv, nullptr, false, h->stream);
@@ -309,13 +342,20 @@ int vthv_dev(S* h, const double* dv) {
 // J' w  (w: device, local rows) -> out (length ld+1), all-reduced
 int jtw_dev(S* h, const double* dw, double* out) {
     if (!h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
+    const bool fused = h->p2p_on;
     {
         EvScope ev(h, 2);
-        CK(mv_launch(MODE_JTW, h->plan, h->J, h->M, nullptr, dw, nullptr, h->partial, out, h->stream));
+        CK(mv_launch(MODE_JTW, h->plan, h->J, h->M, nullptr, dw, nullptr, h->partial, out, h->stream,
+                     fused ? &h->p2p : nullptr, fused ? ++h->p2p_epoch : 0));
     }
-    h->st.kernel_launches += 2;
+    h->st.kernel_launches += fused ? 3 : 2;
     h->st.j_passes += 1;
-    RET(allreduce(h, out, (size_t)h->ld));
+    if (fused) {
+        h->st.allreduces++;
+        h->st.p2p_allreduces++;
+    } else {
+        RET(allreduce(h, out, (size_t)h->ld));
+    }
     h->st.jtw++;
     return BNL_OK;
 }
@@ -856,6 +896,10 @@ void bnl_destroy(bnl_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (int r2 = 0; r2 < kP2PMaxRanks; ++r2)
+        if (h->p2p_opened[r2]) cudaIpcCloseMemHandle(h->p2p_opened[r2]);
+    cudaFree(h->p2p_buf);
+    cudaFree(h->p2p_counter);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_problem(h);
     for (auto& e : h->ev_busy) {
@@ -911,6 +955,62 @@ int bnl_comm_init(bnl_handle h, int nranks, int rank, const void* id128) {
     if (r != ncclSuccess) return h->fail(BNL_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     h->nranks = nranks;
     h->rank = rank;
+    // ---- peer-memory all-reduce over NVLink (p2p.h): exchange CUDA-IPC handles with ncclAllGather ----
+    const char* env = getenv("BNL_P2P_ALLREDUCE");
+    const bool want = !(env && env[0] == '0') && nranks <= kP2PMaxRanks && g_nccl.AllGather != nullptr;
+    int ok = want ? 1 : 0;
+    char* dh = nullptr;
+    std::vector<cudaIpcMemHandle_t> all(nranks);
+    if (want) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        const size_t bytes = std::max<size_t>(p2p_buffer_bytes(nranks), (size_t)4 << 20);
+        cudaIpcMemHandle_t mine;
+        ok = ok && cudaMalloc(&h->p2p_buf, bytes) == cudaSuccess && cudaMemset(h->p2p_buf, 0, bytes) == cudaSuccess &&
+             cudaMalloc(&h->p2p_counter, 256) == cudaSuccess && cudaMemset(h->p2p_counter, 0, 256) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine, h->p2p_buf) == cudaSuccess && cudaMalloc(&dh, (size_t)nranks * 64) == cudaSuccess;
+        if (ok) {
+            cudaMemcpy(dh + (size_t)rank * 64, &mine, 64, cudaMemcpyHostToDevice);
+            ok = g_nccl.AllGather(dh + (size_t)rank * 64, dh, 64, ncclChar, h->comm, h->stream) == ncclSuccess &&
+                 cudaStreamSynchronize(h->stream) == cudaSuccess &&
+                 cudaMemcpy(all.data(), dh, (size_t)nranks * 64, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        for (int r2 = 0; ok && r2 < nranks; ++r2) {
+            void* base = h->p2p_buf;
+            if (r2 != rank) {
+                ok = cudaIpcOpenMemHandle(&base, all[r2], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                if (ok) h->p2p_opened[r2] = base;
+            }
+            h->p2p.mbox[r2] = static_cast<double*>(base);
+            h->p2p.flag[r2] = p2p_flags_of(static_cast<double*>(base), nranks);
+        }
+        cudaGetLastError();
+    }
+    // all ranks must agree (min over ranks); this all-reduce is also the barrier after everyone's memset
+    int* dok = nullptr;
+    if (cudaMalloc(&dok, sizeof(int)) == cudaSuccess) {
+        cudaMemcpy(dok, &ok, sizeof(int), cudaMemcpyHostToDevice);
+        g_nccl.AllReduce(dok, dok, 1, ncclInt, ncclMin, h->comm, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(dok);
+    } else {
+        ok = 0;
+    }
+    if (dh) cudaFree(dh);
+    h->p2p.nranks = nranks;
+    h->p2p.rank = rank;
+    h->p2p.done_counter = h->p2p_counter;
+    h->p2p.timeout_flag = &h->sd->p2p_timeout;
+    h->p2p_on = ok != 0;
+    h->p2p_epoch = 0;
+    return BNL_OK;
+}
+
+int bnl_comm_info(bnl_handle h, int32_t* nranks, int32_t* rank, int32_t* p2p_allreduce) {
+    if (!valid(h)) return BNL_EINVAL;
+    if (nranks) *nranks = h->nranks;
+    if (rank) *rank = h->rank;
+    if (p2p_allreduce) *p2p_allreduce = h->p2p_on ? 1 : 0;
     return BNL_OK;
 }
 

@@ -19,7 +19,8 @@
  *     caller (the reference is not re-entrant either: src/basic_tralcnlss.jl:4, lincons mutated in place).
  *   - there is NO CPU fallback: bnl_create fails with BNL_ENODEV when no sm_100 device is visible.
  *   - multi-GPU: one process (one handle) per GPU; rows of J / r are sharded, every O(n) quantity is
- *     replicated; the only collective is an NCCL all-reduce of n+1 doubles per Hessian apply.
+ *     replicated; the only collective is an all-reduce of n+1 doubles per Hessian apply (fused NVLink
+ *     peer-memory kernels, NCCL as the fallback and for the n^2 Gram).
  */
 #ifndef BENLSIP_B200_H
 #define BENLSIP_B200_H
@@ -81,6 +82,7 @@ typedef struct bnl_stats {
     int64_t j_passes;     /* streaming passes over the Jacobian actually executed                     */
     int64_t gram_count;   /* Gram formations (BNL_HESSIAN_GRAM)                                        */
     double gram_ms;
+    int64_t p2p_allreduces; /* all-reduces done by the fused NVLink peer-memory kernels instead of NCCL       */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */
@@ -116,6 +118,9 @@ int bnl_set_params(bnl_handle h, const bnl_params* p);
 /* ---- multi-GPU (row sharding).  id is an ncclUniqueId (128 bytes). ------------------- */
 int bnl_comm_unique_id(void* id128);
 int bnl_comm_init(bnl_handle h, int nranks, int rank, const void* id128);
+/* p2p_allreduce = 1 when the n+1-double all-reduce runs as fused NVLink peer-memory kernels (CUDA IPC mailboxes;
+ * default when all ranks could map each other; BNL_P2P_ALLREDUCE=0 forces NCCL). */
+int bnl_comm_info(bnl_handle h, int32_t* nranks, int32_t* rank, int32_t* p2p_allreduce);
 
 /* ---- problem: MixedConstraints(A, chol_aat; l, u), src/polyhedral_constraints.jl:9-18, and
  *      chol_aat = cholesky(A*A'), src/basic_tralcnlss.jl:206.  M_local rows [row0,row0+M_local) of
