@@ -429,6 +429,33 @@ def test_native_outer_loop_equals_host_outer_loop(S, tmp_path):
     assert "Outer iter 1" in txt and "AL value" in txt
 
 
+def test_native_outer_loop_with_constraints_matches_host_outer_loop():
+    """bnl_tralcnllss (outer loop inside the library) on the mixed-constraint family: same iterate,
+    multipliers and penalty as the host-side outer loop (least_squares_multipliers, mu / omega / eta updates)."""
+    P = MixedConstraintProblem(600, 24, 4)
+    kw = dict(max_outer_iter=60, max_inner_iter=200)
+    tr = {}
+    x_h, y_h = B.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr, **kw)
+    S2 = B.Solver(0)
+    S2.set_problem(P.M, P.n, P.A, P.xlow, P.xupp, p=1)
+    S2.use_callbacks(P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons)
+    S2.set_params(max_inner_iter=200)
+    x_n, y_n, mu, pix = S2.tralcnllss_native(P.x0, max_outer_iter=60)
+    assert rel(x_n, x_h) < 1e-12 and rel(y_n, y_h) < 1e-10 and mu == tr["mu"]
+    assert np.array_equal(S2.fixvars_words(), tr["fixvars_words"])
+    S2.close()
+
+
+def test_bounds_error_and_dimension_errors(S):
+    S.set_problem(10, 4, None, -np.ones(4), np.ones(4))
+    with pytest.raises(B.DimensionMismatch):
+        S.hess_mul(np.zeros(5))
+    with pytest.raises(ValueError):
+        S.hess_mul(np.zeros(4))  # no Jacobian bound yet
+    with pytest.raises(B.DimensionMismatch):
+        S.set_problem(10, 5000)  # n > 4096 is outside the streaming kernels' range
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Full BASELINE size (cfg3: M = 1e7, n = 1024, 81.9 GB of J): size-independent properties
 # ---------------------------------------------------------------------------------------------------------
