@@ -412,6 +412,7 @@ MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes) {
             p.RB = 2;
         } else {
             p.supported = false;
+            return p;  // ld > 4096: outside the streaming kernels' range
         }
     }
     p.R = p.RB;  // a stage is one RB-row batch of one team

@@ -79,7 +79,7 @@ struct bnl_solver {
     int n = 0, ld = 0, m_lin = 0, p = 0;
     bool mask = true;
 
-    double *J = nullptr, *r = nullptr, *r_trial = nullptr, *ydata = nullptr, *tvec = nullptr, *Jcm = nullptr;
+    double *J = nullptr, *r = nullptr, *r_trial = nullptr, *ydata = nullptr, *tvec = nullptr;
     double* vecpool = nullptr;
     unsigned char* flagpool = nullptr;
     VecCtx vc{};
@@ -427,10 +427,8 @@ int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_o
 
 int upload_colmajor(S* h, const double* src, long long rows, int cols, long long lds, double* dst_rowmajor, int ldd) {
     // stage the column-major host matrix through pinned memory into a device column-major buffer, then transpose
+    // only host-supplied matrices (callback mode, small configs) pay for this temporary second buffer
     const size_t total = (size_t)rows * cols;
-    if (!h->Jcm || true) {
-        // (re)allocate lazily: only host-supplied Jacobians (small configs) pay for this second buffer
-    }
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, std::max<size_t>(total, 1) * sizeof(double)));
     const size_t chunk = 1 << 20;  // doubles per pinned chunk
