@@ -30,7 +30,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 CFG = {"cfg3": dict(M=10_000_000, n=1024, model="glm", seed=3, noise=1e-3, cond_exp=0.0),
-       "cfg2": dict(M=1_000_000, n=256, model="expsum", seed=1, noise=1e-3, cond_exp=0.0)}
+       "cfg2": dict(M=1_000_000, n=256, model="expsum", seed=1, noise=1e-3, cond_exp=0.0),
+       # BASELINE config[3]: linear equalities + nonlinear (sphere) equality + box, AL loop exercised; general projection
+       "cfg4": dict(M=4_000_000, n=2048, model="glm_mixed", m_lin=64, seed=5, noise=1e-3, cond_exp=0.0)}
 METRIC = "matvec_equiv_GBps"
 UNIT = "GB/s"
 
@@ -151,8 +153,19 @@ def run_ours(args, cfg):
     need = 8.0 * M_loc * n * 1.02 + 3 * 8.0 * M_loc + (1 << 30)
     if need > info["free_bytes"]:
         raise SystemExit(f"J shard ({need/1e9:.1f} GB) does not fit the GPU ({info['free_bytes']/1e9:.1f} GB free)")
-    S.set_problem(M_loc, n, M_total=M, row0=row0)
-    S.use_builtin_model(B.MODEL_GLM if cfg["model"] == "glm" else B.MODEL_EXPSUM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
+    solve_kw = {}
+    if cfg["model"] == "glm_mixed":
+        from benlsip_b200.problems import mixed_constraint_setup
+        n = args.n or n
+        mc = mixed_constraint_setup(n, args.m_lin or cfg["m_lin"], cfg["seed"])
+        S.set_problem(M_loc, n, mc["A"], mc["xlow"], mc["xupp"], p=1, M_total=M, row0=row0)
+        S.use_builtin_model(B.MODEL_GLM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
+        S.model_set_truth(mc["x_star"], mc["x0"])
+        S.use_builtin_nlcons(B.NLCONS_SPHERE, mc["rho2"])
+        solve_kw = dict(max_outer_iter=args.max_outer or 500, max_inner_iter=args.max_inner or 500)
+    else:
+        S.set_problem(M_loc, n, M_total=M, row0=row0)
+        S.use_builtin_model(B.MODEL_GLM if cfg["model"] == "glm" else B.MODEL_EXPSUM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
     if world > 1:
         init_solver_comm(S)
     x0 = S.model_vectors()["x0"]
@@ -168,7 +181,7 @@ def run_ours(args, cfg):
         tr = {}
         S.reset_stats()
         t0 = time.perf_counter()
-        x, _ = B.tralcnllss(x0, None, None, None, None, None, None, None, None, solver=S, trace=tr)  # public API, host buffers
+        x, _ = B.tralcnllss(x0, None, None, None, None, None, None, None, None, solver=S, trace=tr, **solve_kw)  # public API, host buffers
         wall = time.perf_counter() - t0
         return x, tr, wall
 
@@ -201,7 +214,7 @@ def run_ours(args, cfg):
     # extra: one solve in the opt-in Gram-apply mode (G = J'J on the FP64 tensor cores once per Jacobian), reported beside
     # the headline, never mixed into it
     gram_extra = None
-    if args.hessian == "matrix_free" and not args.no_gram_extra:
+    if args.hessian == "matrix_free" and not args.no_gram_extra and cfg["model"] != "glm_mixed":
         S.set_hessian_mode(B.HESSIAN_GRAM)
         step()  # warm-up (allocations)
         barrier()
@@ -244,10 +257,10 @@ def run_ours(args, cfg):
                 "counts": {"outer": tr["outer_iters"], "inner": tr["stats"]["inner_iters"], "minor": tr["stats"]["minor_iters"],
                            "cg": tr["stats"]["cg_iters"], "breakpoints": tr["stats"]["breakpoints"], "hess_mul": tr["stats"]["hess_mul"],
                            "vthv": tr["stats"]["vthv"], "jtw": tr["stats"]["jtw"], "jac_eval": tr["stats"]["jac_eval"],
+                           "chol_rebuilds": tr["stats"]["chol_rebuilds"], "mu": tr["mu"],
                            "res_eval": tr["stats"]["res_eval"], "allreduces": tr["stats"]["allreduces"],
                            "p2p_allreduces": tr["stats"]["p2p_allreduces"]},
-                "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"])),
-                          "x_err_inf_vs_true_interior": None},
+                "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"]))},
                 "roofline": {"bound": "hbm", "kernel": "mv_stream_kernel<JTJV> (fused J'(Jv), one pass)", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                              "avg_launch_ms": avg_ms, "launches_timed": hm_cnt, "algorithmic_bytes_per_launch": alg_bytes,
@@ -272,6 +285,8 @@ def run_ours(args, cfg):
 
 def cpu_baseline(args, cfg):
     """Oracle ('port') timed on this host's cores on a bounded row sample of the same workload (~10-30 s)."""
+    if cfg["model"] == "glm_mixed":
+        return None
     from oracle import benlsip_oracle as O
     from oracle.models import ExpSumProblem, GlmProblem
 
@@ -302,6 +317,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=sorted(CFG))
     ap.add_argument("--M", type=int, default=0, help="override the row count (debug)")
+    ap.add_argument("--n", type=int, default=0, help="override n (cfg4 only, debug)")
+    ap.add_argument("--m-lin", type=int, default=0, dest="m_lin")
+    ap.add_argument("--max-outer", type=int, default=0, dest="max_outer")
+    ap.add_argument("--max-inner", type=int, default=0, dest="max_inner")
     ap.add_argument("--cpu-sample-div", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hessian", default="matrix_free", choices=["matrix_free", "gram"],

@@ -28,6 +28,7 @@ SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)
 CG_SOLVED, CG_BOUND_HIT, CG_NEGATIVE_CURVATURE, CG_MAX_ITER, CG_NOTHING = 0, 1, 2, 3, -1
 MODEL_GLM, MODEL_EXPSUM = 1, 2
 HESSIAN_MATRIX_FREE, HESSIAN_GRAM = 0, 1
+NLCONS_SPHERE = 1
 
 
 class BnlError(RuntimeError):
@@ -112,6 +113,8 @@ def load_library(build_if_missing: bool = False):
         "bnl_use_builtin_model": ([H, i32, _DP, i32, C.c_uint32], C.c_int),
         "bnl_use_callbacks": ([H, CALLBACK, CALLBACK, CALLBACK, CALLBACK, C.c_void_p], C.c_int),
         "bnl_model_vectors": ([H, _DP, _DP, _DP, _DP], C.c_int),
+        "bnl_use_builtin_nlcons": ([H, i32, _DP, i32], C.c_int), "bnl_model_set_truth": ([H, _DP, _DP], C.c_int),
+        "bnl_nlcons": ([H, _DP, _DP, _DP], C.c_int), "bnl_gradient": ([H, _DP, _DP], C.c_int),
         "bnl_upload_jacobian": ([H, _DP, i64], C.c_int), "bnl_upload_nlcons_jacobian": ([H, _DP, i64], C.c_int),
         "bnl_set_mu": ([H, dbl], C.c_int), "bnl_eval_jacobian": ([H, _DP], C.c_int),
         "bnl_residuals": ([H, _DP, _DP, _DP], C.c_int), "bnl_hess_mul": ([H, _DP, _DP], C.c_int),
@@ -237,6 +240,28 @@ class Solver:
     def use_builtin_model(self, model_id, noise=1e-3, cond_exp=0.0, seed=3):
         prm = np.array([noise, cond_exp], dtype=np.float64)
         self._ck(self.lib.bnl_use_builtin_model(self.h, model_id, _p(prm), 2, seed))
+
+    def use_builtin_nlcons(self, kind, rho2):
+        prm = np.array([rho2], dtype=np.float64)
+        self._ck(self.lib.bnl_use_builtin_nlcons(self.h, int(kind), _p(prm), 1))
+
+    def model_set_truth(self, x_true, x0=None):
+        xt = _vec(x_true, self.n)
+        x0v = _vec(x0, self.n) if x0 is not None else None
+        self._ck(self.lib.bnl_model_set_truth(self.h, _p(xt), _p(x0v)))
+
+    def nlcons(self, x):
+        """`nlconstraints(x)`, `jac_nlcons(x)` (built-in or callbacks) -> (c, C)."""
+        c = np.zeros(self.p)
+        Cm = np.zeros((self.p, self.n), order="F")
+        self._ck(self.lib.bnl_nlcons(self.h, _p(_vec(x, self.n)), _p(c), _p(Cm)))
+        return c, np.ascontiguousarray(Cm)
+
+    def gradient(self, x):
+        """`jac_res(x)' * residuals(x)` (src/basic_tralcnlss.jl:893)."""
+        g = np.empty(self.n)
+        self._ck(self.lib.bnl_gradient(self.h, _p(_vec(x, self.n)), _p(g)))
+        return g
 
     def model_vectors(self):
         out = [np.empty(self.n) for _ in range(4)]
@@ -506,9 +531,8 @@ def tralcnllss(x0, residuals, jac_res, nlconstraints, jac_nlcons, A, b, x_l, x_u
     omega, eta = initial_tolerances(mu0, omega0, eta0, k_crit, k_feas)  # :229
     # least_squares_multipliers :887-903
     if p > 0:
-        S.eval_jacobian(x)
-        g = S.jtw(np.asarray(residuals(x), dtype=np.float64))
-        Cm = np.asarray(jac_nlcons(x), dtype=np.float64)
+        g = S.gradient(x)  # jac_res(x)' * residuals(x) on the device
+        Cm = S.nlcons(x)[1] if builtin else np.asarray(jac_nlcons(x), dtype=np.float64)
         L = np.linalg.cholesky(Cm @ Cm.T)
         y = np.linalg.solve(L.T, np.linalg.solve(L, -(Cm @ g)))
     else:

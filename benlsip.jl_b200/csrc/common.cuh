@@ -36,6 +36,7 @@ struct Scal {
     double jv_sumsq;           // dot(Jv,Jv) (global)
     double cdot_yc, cdot_cc;   // dot(y,cx), dot(cx,cx)
     double Cv_sumsq;           // dot(Cv,Cv)
+    double c0;                 // built-in nonlinear constraint value c(x) (p = 1)
     int chol_fail;             // device Cholesky hit a non-positive pivot
     int p2p_timeout;           // peer-memory all-reduce gave up waiting for a rank
 };

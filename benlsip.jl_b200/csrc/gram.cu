@@ -6,7 +6,7 @@
 //
 // Tiling: CTA = 128x128 output tile (upper-triangular tile pairs only) x one split-K slice of rows; 8 warps,
 // warp tile 64x32 = 8x4 m8n8k4 tiles (64 FP64 accumulators / thread).  J rows are staged by a 3-stage cp.async
-// (LDGSTS) ring of 16-row chunks; smem row stride 132 doubles => conflict-free 64-bit operand loads.
+// (LDGSTS) ring of 32-row chunks; smem row stride 132 doubles => conflict-free 64-bit operand loads.
 // Split-K partials are summed in fixed order (deterministic), the lower triangle is mirrored.
 #include "common.cuh"
 #include "gram.h"
@@ -15,7 +15,7 @@ namespace bnl {
 namespace {
 
 constexpr int TB = 128;       // output tile edge
-constexpr int KT = 16;        // rows per smem chunk
+constexpr int KT = 32;        // rows per smem chunk
 constexpr int LDS_ = TB + 4;  // padded smem row stride (doubles)
 constexpr int NSTG = 3;       // cp.async stages
 constexpr int kGramSmem = NSTG * 2 * KT * LDS_ * (int)sizeof(double);

@@ -108,6 +108,8 @@ struct bnl_solver {
     bnl_callback cb_res = nullptr, cb_jac = nullptr, cb_nl = nullptr, cb_jnl = nullptr;
     void* cb_ctx = nullptr;
     bool have_J = false;
+    int nl_kind = 0;       // built-in nonlinear constraint (BNL_NLCONS_*), 0 = none / callbacks
+    double nl_rho2 = 0.0;
 
     // host staging
     double* pin = nullptr;
@@ -405,6 +407,13 @@ int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_o
         EvScope ev(h, 3);
         CK(model_residual(margs(h), dx, h->ydata, rbuf, h->sumsq_partial, h->sumsq_blocks, &h->sd->sumsq_r, h->stream));
         h->st.kernel_launches += 2;
+        if (h->p > 0) {  // built-in nlconstraints(x): the p-vector lives on the host, like the reference's closure result
+            if (h->nl_kind != BNL_NLCONS_SPHERE) return h->fail(BNL_EINVAL, "p > 0 with a built-in model needs bnl_use_builtin_nlcons");
+            vk_sphere_value(h->vc, dx, h->nl_rho2, h->stream);
+            KLAUNCH();
+            CK(cudaStreamSynchronize(h->stream));
+            c_out[0] = h->sh->c0;
+        }
     } else {
         if (!h->cb_res) return h->fail(BNL_EINVAL, "no model bound");
         h->h_x.resize(h->n);
@@ -451,9 +460,17 @@ int upload_colmajor(S* h, const double* src, long long rows, int cols, long long
 // jac_res(x), jac_nlcons(x): fills J (and C in callback mode)
 int eval_jacobian(S* h, const double* dx) {
     if (h->model_id != 0) {
-        EvScope ev(h, 4);
-        CK(model_jacobian(margs(h), dx, h->J, h->stream));
-        KLAUNCH();
+        {
+            EvScope ev(h, 4);
+            CK(model_jacobian(margs(h), dx, h->J, h->stream));
+            KLAUNCH();
+        }
+        if (h->p > 0) {  // built-in jac_nlcons(x)
+            if (h->nl_kind != BNL_NLCONS_SPHERE) return h->fail(BNL_EINVAL, "p > 0 with a built-in model needs bnl_use_builtin_nlcons");
+            vk_sphere_jac(h->vc, dx, h->stream);
+            vk_scale_C(h->vc, h->stream);
+            h->st.kernel_launches += 2;
+        }
     } else {
         if (!h->cb_jac) return h->fail(BNL_EINVAL, "no model bound");
         h->h_x.resize(h->n);
@@ -791,6 +808,7 @@ int free_problem(S* h) {
     h->problem_set = false;
     h->have_J = false;
     h->model_id = 0;
+    h->nl_kind = 0;
     return BNL_OK;
 }
 
@@ -1112,7 +1130,7 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
 
 int bnl_use_builtin_model(bnl_handle h, int32_t model_id, const double* params, int32_t nparams, uint32_t seed) {
     if (!valid(h) || !h->problem_set) return BNL_EINVAL;
-    if (h->p != 0) return h->fail(BNL_EINVAL, "builtin models have no nonlinear constraints (p must be 0)");
+    if (h->p > 1) return h->fail(BNL_EINVAL, "built-in models support at most one (built-in) nonlinear constraint");
     CK(cudaSetDevice(h->device));
     const int n = h->n;
     h->seed = seed;
@@ -1186,6 +1204,28 @@ int bnl_use_callbacks(bnl_handle h, bnl_callback residuals, bnl_callback jac_res
     return BNL_OK;
 }
 
+int bnl_use_builtin_nlcons(bnl_handle h, int32_t kind, const double* params, int32_t nparams) {
+    if (!valid(h) || !h->problem_set) return BNL_EINVAL;
+    if (kind != BNL_NLCONS_SPHERE || nparams < 1 || !params) return h->fail(BNL_EINVAL, "unknown built-in nonlinear constraint");
+    if (h->p != 1) return h->fail(BNL_EDIM, "the sphere constraint needs p == 1");
+    h->nl_kind = kind;
+    h->nl_rho2 = params[0];
+    return BNL_OK;
+}
+
+int bnl_model_set_truth(bnl_handle h, const double* x_true, const double* x0) {
+    if (!valid(h) || h->model_id == 0 || !x_true) return BNL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    std::copy(x_true, x_true + h->n, h->m_xtrue.begin());
+    if (x0) std::copy(x0, x0 + h->n, h->m_x0.begin());
+    RET(put_vec(h, h->m_xtrue.data(), h->d_xtrue, h->n));
+    CK(model_setup_y(margs(h), h->d_xtrue, h->ydata, h->stream));  // y = model(x_true) + noise
+    KLAUNCH();
+    RET(sync(h));
+    h->have_J = false;
+    return BNL_OK;
+}
+
 int bnl_model_vectors(bnl_handle h, double* x0, double* xlow, double* xupp, double* x_true) {
     if (!valid(h) || h->model_id == 0) return BNL_EINVAL;
     const size_t nb = (size_t)h->n * sizeof(double);
@@ -1246,6 +1286,38 @@ int bnl_residuals(bnl_handle h, const double* x, double* r_local, double* sumsq)
     RET(sync(h));
     if (sumsq) *sumsq = h->sh->sumsq_r;
     if (r_local && h->M > 0) RET(get_vec(h, h->r_trial, r_local, h->M));
+    return BNL_OK;
+}
+
+int bnl_nlcons(bnl_handle h, const double* x, double* c, double* C_colmajor) {
+    ENTER();
+    if (h->p == 0) return BNL_OK;
+    if (h->model_id != 0) {
+        if (h->nl_kind != BNL_NLCONS_SPHERE) return h->fail(BNL_EINVAL, "no built-in nonlinear constraint bound");
+        RET(put_vec(h, x, h->vc.t2, h->n));
+        vk_sphere_value(h->vc, h->vc.t2, h->nl_rho2, h->stream);
+        RET(sync(h));
+        if (c) c[0] = h->sh->c0;
+        if (C_colmajor)
+            for (int j = 0; j < h->n; ++j) C_colmajor[j] = 2.0 * x[j];  // p = 1: column-major 1 x n
+    } else {
+        if (!h->cb_nl || !h->cb_jnl) return h->fail(BNL_EINVAL, "no nonlinear-constraint callbacks bound");
+        if (c && h->cb_nl(x, c, h->cb_ctx) != 0) return h->fail(BNL_ECALLBACK, "nlconstraints callback failed");
+        if (C_colmajor && h->cb_jnl(x, C_colmajor, h->cb_ctx) != 0) return h->fail(BNL_ECALLBACK, "jac_nlcons callback failed");
+    }
+    return BNL_OK;
+}
+
+int bnl_gradient(bnl_handle h, const double* x, double* g) {  // jac_res(x)' * residuals(x)   :893
+    ENTER();
+    if (!x || !g) return BNL_EINVAL;
+    RET(put_vec(h, x, h->vc.t2, h->n));
+    std::vector<double> cdummy;
+    RET(eval_residual(h, h->vc.t2, h->r_trial, cdummy));
+    RET(eval_jacobian(h, h->vc.t2));
+    RET(jtw_dev(h, h->r_trial, h->vc.hv));
+    RET(sync(h));
+    RET(get_vec(h, h->vc.hv, g, h->n));
     return BNL_OK;
 }
 
@@ -1628,12 +1700,10 @@ int bnl_tralcnllss(bnl_handle h, const double* x0, const bnl_outer_params* op_in
         if (rc == BNL_OK) rc = jtw_dev(h, h->r, h->vc.hv);
         if (rc == BNL_OK) rc = sync(h);
         if (rc == BNL_OK) rc = get_vec(h, h->vc.hv, g.data(), n);
+        std::vector<double> Cjac((size_t)p * n);
+        if (rc == BNL_OK) rc = bnl_nlcons(h, x.data(), nullptr, Cjac.data());
         if (rc == BNL_OK) {
-            h->h_tmp.resize((size_t)p * n);
-            if (h->cb_jnl(x.data(), h->h_tmp.data(), h->cb_ctx) != 0) rc = h->fail(BNL_ECALLBACK, "jac_nlcons callback failed");
-        }
-        if (rc == BNL_OK) {
-            const double* C = h->h_tmp.data();  // column-major p x n
+            const double* C = Cjac.data();  // column-major p x n
             std::vector<double> CCt((size_t)p * p, 0.0), b(p, 0.0);
             for (int i = 0; i < p; ++i) {
                 for (int j = 0; j < p; ++j) {

@@ -371,6 +371,17 @@ __global__ void k_active_flags(VecCtx c, const double* x, const double* s, doubl
 }
 
 __global__ void k_publish(Scal* sd, Scal* sh) { publish(sd, sh); }
+__global__ void k_sphere_value(VecCtx c, const double* x, double rho2) {
+    __shared__ double shd[32];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < c.n; i += blockDim.x) a = fma(x[i], x[i], a);
+    a = block_sum(a, shd);
+    if (threadIdx.x == 0) c.sd->c0 = a - rho2;
+    publish(c.sd, c.sh);
+}
+__global__ void k_sphere_jac(VecCtx c, const double* x) {
+    for (int i = threadIdx.x; i < c.n; i += blockDim.x) c.C[i] = 2.0 * x[i];
+}
 __global__ void k_mask_project(VecCtx c, const double* src, double* dst) {
     for (int i = threadIdx.x; i < c.n; i += blockDim.x) dst[i] = c.fix[i] ? 0.0 : src[i];
 }
@@ -643,6 +654,8 @@ void vk_list_flags(const unsigned char* flags, int n, long long* idx_out, int* c
     k_list_flags<<<1, kVT, 0, st>>>(flags, n, idx_out, count_out);
 }
 void vk_mask_project(const VecCtx& c, const double* src, double* dst, cudaStream_t st) { k_mask_project<<<1, kVT, 0, st>>>(c, src, dst); }
+void vk_sphere_value(const VecCtx& c, const double* x, double rho2, cudaStream_t st) { k_sphere_value<<<1, kVT, 0, st>>>(c, x, rho2); }
+void vk_sphere_jac(const VecCtx& c, const double* x, cudaStream_t st) { k_sphere_jac<<<1, kVT, 0, st>>>(c, x); }
 void vk_publish(Scal* sd, Scal* sh, cudaStream_t st) { k_publish<<<1, 64, 0, st>>>(sd, sh); }
 void vk_active_flags(const VecCtx& c, const double* x, const double* s, double delta, cudaStream_t st) {
     k_active_flags<<<1, kVT, 0, st>>>(c, x, s, delta);

@@ -46,6 +46,9 @@ void vk_unpack_fix(const unsigned long long* words, int n, unsigned char* fix, S
 void vk_set_flags(const VecCtx& c, const long long* idx, int count, cudaStream_t st);  // fix[idx] = 1, recount
 void vk_list_flags(const unsigned char* flags, int n, long long* idx_out, int* count_out, cudaStream_t st);
 void vk_mask_project(const VecCtx& c, const double* src, double* dst, cudaStream_t st);  // dst = fix ? 0 : src
+// built-in nonlinear constraint  c(x) = x'x - rho2  (p = 1):  value -> sd->c0 ;  jac_nlcons(x) = 2x' -> C row 0
+void vk_sphere_value(const VecCtx& c, const double* x, double rho2, cudaStream_t st);
+void vk_sphere_jac(const VecCtx& c, const double* x, cudaStream_t st);
 void vk_publish(Scal* sd, Scal* sh, cudaStream_t st);
 void vk_active_flags(const VecCtx& c, const double* x, const double* s, double delta, cudaStream_t st);  // at[] only
 

@@ -98,6 +98,8 @@ enum { BNL_HESSIAN_MATRIX_FREE = 0, BNL_HESSIAN_GRAM = 1 };
 
 /* Built-in device-side models (definitions in oracle/models.py, the executable spec). */
 enum { BNL_MODEL_GLM = 1, BNL_MODEL_EXPSUM = 2 };
+/* Built-in nonlinear equality constraint (p = 1) for the device models: c(x) = x'x - rho2, params = {rho2}. */
+enum { BNL_NLCONS_SPHERE = 1 };
 
 /* User callbacks (the reference's `residuals, jac_res, nlconstraints, jac_nlcons` closures,
  * src/basic_tralcnlss.jl:167-176), e.g. Julia `@cfunction`.  Matrices are written column-major.
@@ -135,6 +137,8 @@ int bnl_use_builtin_model(bnl_handle h, int32_t model_id, const double* params, 
 int bnl_use_callbacks(bnl_handle h, bnl_callback residuals, bnl_callback jac_res, bnl_callback nlconstraints,
                       bnl_callback jac_nlcons, void* ctx);
 int bnl_model_vectors(bnl_handle h, double* x0, double* xlow, double* xupp, double* x_true); /* builtin only */
+int bnl_use_builtin_nlcons(bnl_handle h, int32_t kind, const double* params, int32_t nparams);
+int bnl_model_set_truth(bnl_handle h, const double* x_true, const double* x0 /*or NULL*/); /* regenerates the data y */
 
 /* ---- AlHessian (src/basic_tralcnlss.jl:6-10): the handle holds the current (J, C, mu) -------------- */
 int bnl_upload_jacobian(bnl_handle h, const double* J_colmajor, int64_t ldj);  /* pinned async H2D + transpose */
@@ -142,6 +146,8 @@ int bnl_upload_nlcons_jacobian(bnl_handle h, const double* C_colmajor, int64_t l
 int bnl_set_mu(bnl_handle h, double mu);
 int bnl_eval_jacobian(bnl_handle h, const double* x);            /* jac_res(x), jac_nlcons(x) via model/callbacks */
 int bnl_residuals(bnl_handle h, const double* x, double* r_local /*or NULL*/, double* sumsq /*global*/);
+int bnl_nlcons(bnl_handle h, const double* x, double* c, double* C_colmajor); /* nlconstraints(x), jac_nlcons(x) :41-42 */
+int bnl_gradient(bnl_handle h, const double* x, double* g);      /* jac_res(x)'*residuals(x)  :893 */
 int bnl_hess_mul(bnl_handle h, const double* v, double* Hv);     /* Base.:*(H,v)   :102-106 */
 int bnl_vthv(bnl_handle h, const double* v, double* out);        /* vthv(H,v)      :92-96   */
 int bnl_jv(bnl_handle h, const double* v, double* Jv_local);     /* H.J*v          :93,:103 */

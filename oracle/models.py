@@ -253,7 +253,7 @@ class MixedConstraintProblem:
         self.M, self.n, self.m_lin, self.seed = int(M), int(n), int(m_lin), int(seed)
         i = np.arange(M, dtype=np.uint64)
         j = np.arange(n)
-        self.Ad = sym(seed, i, j) / np.sqrt(float(n))
+        self.Ad = sym(seed, i, j) * glm_col_scale(n, 0.0)[None, :]  # == the device GLM design with the same seed
         self.A = sym(seed + 7, np.arange(m_lin, dtype=np.uint64), j)
         z0 = np.zeros(1, dtype=np.uint64)
         self.x_star = 0.6 * sym(seed + 2, z0, j)[0]

@@ -360,6 +360,32 @@ def test_cfg4_family_mixed_constraints_full_solve_parity():
     assert st["chol_rebuilds"] > 0
 
 
+def test_cfg4_family_on_device_matches_oracle(S):
+    """cfg4 family with NO host callbacks: device GLM residual/Jacobian generators (truth vector supplied), built-in sphere
+    constraint (bnl_use_builtin_nlcons), linear equalities A from the host once (bnl_set_problem), general projection on
+    the device.  Same problem as MixedConstraintProblem => exact counts against the oracle."""
+    P = MixedConstraintProblem(600, 24, 4)
+    S.set_problem(P.M, P.n, P.A, P.xlow, P.xupp, p=1)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, P.seed)
+    S.model_set_truth(P.x_star, P.x0)
+    S.use_builtin_nlcons(B.NLCONS_SPHERE, P.rho2)
+    r, ss = S.residuals(P.x0)
+    assert np.max(np.abs(r - P.residuals(P.x0))) < 1e-13
+    c, Cm = S.nlcons(P.x0)
+    assert abs(c[0] - P.nlconstraints(P.x0)[0]) < 1e-13 and np.allclose(Cm, P.jac_nlcons(P.x0), rtol=0, atol=0)
+    assert rel(S.gradient(P.x0), P.jac_res(P.x0).T @ P.residuals(P.x0)) < 1e-12
+    kw = dict(max_outer_iter=60, max_inner_iter=200)
+    tr_o, tr_g = {}, {}
+    x_o, y_o = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr_o, **kw)
+    x_g, y_g = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr_g, **kw)
+    st = tr_g["stats"]
+    assert (tr_g["outer_iters"], st["inner_iters"], st["cg_iters"], st["breakpoints"]) == \
+           (tr_o["outer_iters"], tr_o["inner_iters"], tr_o.get("cg_iters", 0), tr_o.get("breakpoints", 0))
+    assert tr_g["mu"] == tr_o["mu"]
+    assert rel(x_g, x_o) < 1e-10 and rel(y_g, y_o) < 1e-8
+    assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+
+
 def test_cfg5_family_ill_conditioned_inner_steps(S):
     """cfg5 family (column scaling 10^(-6 j/n), kappa(J'J) ~ 1e12), shrunk.  The reference algorithm does not reach its
     tolerance on this family in any reasonable number of iterations (oracle: 20 outer x 100 inner x ~50 CG at n = 64), so
