@@ -171,7 +171,102 @@ __global__ void k_project(DenseCtx c, const double* r, double* v, int negate) {
     for (int j = threadIdx.x; j < c.n; j += blockDim.x) v[j] = sgn * r[j] - v[j];
 }
 
+// ---- reduced-space projection --------------------------------------------------------------------------------
+// Lr = cholesky(A_free A_free').L   (m x m, column-major, global memory; factorisation by warp 0)
+__global__ void k_rs_rebuild(DenseCtx c, const unsigned char* fix) {
+    const int m = c.m;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int j = e / m, i = e % m;
+        double s = 0.0;
+        if (i >= j) {
+            const double* ai = c.A + (size_t)i * c.ld;
+            const double* aj = c.A + (size_t)j * c.ld;
+            for (int k = 0; k < c.n; ++k)
+                if (!fix[k]) s = fma(ai[k], aj[k], s);
+        }
+        c.Lr[(size_t)j * m + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int k = 0; k < m; ++k) {
+            const double akk = c.Lr[(size_t)k * m + k];
+            if (!(akk > 0.0)) {
+                if (lane == 0) c.sd->chol_fail = 1;
+                break;
+            }
+            const double lkk = sqrt(akk);
+            __syncwarp();
+            for (int i = k + lane; i < m; i += 32) {
+                const double v = c.Lr[(size_t)k * m + i];
+                c.Lr[(size_t)k * m + i] = (i == k) ? lkk : v / lkk;
+            }
+            __syncwarp();
+            for (int j = k + 1; j < m; ++j) {
+                const double ljk = c.Lr[(size_t)k * m + j];
+                for (int i = j + lane; i < m; i += 32) c.Lr[(size_t)j * m + i] -= c.Lr[(size_t)k * m + i] * ljk;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int nwords = sizeof(Scal) / 8;
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(c.sd);
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(c.sh);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) d[i] = s[i];
+}
+
+__global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double* r, double* v, int negate) {
+    const int m = c.m;
+    const double sgn = negate ? -1.0 : 1.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* y = c.ywork;
+    // t = A_free r_free
+    for (int i = warp; i < m; i += nw) {
+        double s = 0.0;
+        for (int j = lane; j < c.n; j += 32)
+            if (!fix[j]) s = fma(c.A[(size_t)i * c.ld + j], sgn * r[j], s);
+        s = warp_sum(s);
+        if (lane == 0) y[i] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // Lr y' = t ; Lr' w = y'   (warp 0, column-oriented forward, row-oriented backward)
+        for (int k = 0; k < m; ++k) {
+            const double yk = y[k] / c.Lr[(size_t)k * m + k];
+            __syncwarp();
+            if (lane == 0) y[k] = yk;
+            for (int i = k + 1 + lane; i < m; i += 32) y[i] -= c.Lr[(size_t)k * m + i] * yk;
+            __syncwarp();
+        }
+        for (int k = m - 1; k >= 0; --k) {
+            double s = 0.0;
+            for (int i = k + 1 + lane; i < m; i += 32) s = fma(c.Lr[(size_t)k * m + i], y[i], s);
+            s = warp_sum(s);
+            __syncwarp();
+            if (lane == 0) y[k] = (y[k] - s) / c.Lr[(size_t)k * m + k];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // v_free = r_free - A_free' w ; v_F = 0
+    for (int j = threadIdx.x; j < c.n; j += blockDim.x) {
+        double out = 0.0;
+        if (!fix[j]) {
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s = fma(c.A[(size_t)i * c.ld + j], y[i], s);
+            out = sgn * r[j] - s;
+        }
+        v[j] = out;
+    }
+}
+
 }  // namespace
+
+void dk_rs_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st) { k_rs_rebuild<<<1, kDT, 0, st>>>(c, fix); }
+void dk_rs_project(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, bool negate, cudaStream_t st) {
+    k_rs_project<<<1, kDT, 0, st>>>(c, fix, r, v, negate ? 1 : 0);
+}
 
 void dk_chol_aat(const DenseCtx& c, cudaStream_t st) { k_chol_aat<<<1, kDT, 0, st>>>(c); }
 void dk_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st) { k_rebuild<<<1, kDT, 0, st>>>(c, fix); }

@@ -15,6 +15,7 @@ struct DenseCtx {
     double* L;             // cap x cap column-major lower factor of A~ A~'  (dim m+q)
     double* G;             // m x cap column-major:  L_A \ A[:,fix]
     double* ywork;         // cap
+    double* Lr;            // m x m column-major lower factor of A_free A_free'  (reduced-space projection)
     long long* fixidx;     // ascending indices of fixed variables (cap)
     int* q_dev;            // number of fixed variables
     Scal* sd;
@@ -24,5 +25,14 @@ struct DenseCtx {
 void dk_chol_aat(const DenseCtx& c, cudaStream_t st);                              // LA = cholesky(A*A').L  (basic_tralcnlss.jl:206)
 void dk_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st);     // update_chol!  :62-68
 void dk_project(const DenseCtx& c, const double* r, double* v, bool negate, cudaStream_t st);  // projection! :158-170
+
+// Reduced-space form of the same projection (default on the solve path).  A~A~' = [AA' A_F; A_F' I] and
+// S = I - G'G is a rank-m downdate of the identity, so P(r) = r - A~'(A~A~')^{-1}A~ r is equivalently
+//     v_F = 0,   v_free = r_free - A_free' (A_free A_free')^{-1} A_free r_free
+// which needs only the m x m Cholesky factor of A_free A_free' (O(m^2 n) per active-set change instead of the
+// reference's O(q^3) rebuild, src/polyhedral_constraints.jl:51 flags that cost).  Same mathematics, same failure
+// condition (A_free rank deficient <=> PosDefException), different rounding.
+void dk_rs_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st);
+void dk_rs_project(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, bool negate, cudaStream_t st);
 
 }  // namespace bnl

@@ -78,6 +78,7 @@ struct bnl_solver {
     long long M = 0, M_total = 0, row0 = 0;
     int n = 0, ld = 0, m_lin = 0, p = 0;
     bool mask = true;
+    bool literal_proj = false;  // BNL_LITERAL_PROJECTION=1: the reference's block factor on the solve path too
 
     double *J = nullptr, *r = nullptr, *r_trial = nullptr, *ydata = nullptr, *tvec = nullptr;
     double* vecpool = nullptr;
@@ -365,7 +366,10 @@ int jtw_dev(S* h, const double* dw, double* out) {
 // ---- projection / active set (general path hooks) --------------------------------------------------------
 int rebuild_chol(S* h) {  // update_chol! :62-68 (general path only; for m_lin == 0 the factor is I: nothing to do)
     if (h->mask) return BNL_OK;
-    dk_rebuild(h->dc, h->vc.fix, h->stream);
+    if (h->literal_proj)
+        dk_rebuild(h->dc, h->vc.fix, h->stream);  // the reference's (m+q)^2 block factor, O(q^3)
+    else
+        dk_rs_rebuild(h->dc, h->vc.fix, h->stream);  // m x m factor of A_free A_free' (dense.h)
     KLAUNCH();
     h->st.chol_rebuilds++;
     return BNL_OK;
@@ -379,7 +383,10 @@ int check_chol(S* h) {  // after a sync
 }
 // v = P(+-r) into dst (general path); mask path is fused into the vec kernels, except for the fine-grained ABI
 int project_general(S* h, const double* src, double* dst, bool negate) {
-    dk_project(h->dc, src, dst, negate, h->stream);
+    if (h->literal_proj)
+        dk_project(h->dc, src, dst, negate, h->stream);
+    else
+        dk_rs_project(h->dc, h->vc.fix, src, dst, negate, h->stream);
     KLAUNCH();
     return BNL_OK;
 }
@@ -795,6 +802,7 @@ int free_problem(S* h) {
     cudaFree(h->dc.L);
     cudaFree(h->dc.G);
     cudaFree(h->dc.ywork);
+    cudaFree(h->dc.Lr);
     cudaFree(h->dc.fixidx);
     cudaFree(h->dc.q_dev);
     h->J = h->r = h->r_trial = h->ydata = h->tvec = h->vecpool = h->partial = h->sumsq_partial = nullptr;
@@ -1111,6 +1119,11 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
         CK(cudaMalloc(&h->dc.L, (size_t)n * n * sizeof(double)));
         CK(cudaMalloc(&h->dc.G, (size_t)m_lin * n * sizeof(double)));
         CK(cudaMalloc(&h->dc.ywork, (size_t)(n + 16) * sizeof(double)));
+        CK(cudaMalloc(&h->dc.Lr, (size_t)m_lin * m_lin * sizeof(double)));
+        {
+            const char* env = getenv("BNL_LITERAL_PROJECTION");
+            h->literal_proj = env && env[0] == '1';
+        }
         CK(cudaMalloc(&h->dc.fixidx, (size_t)(n + 16) * sizeof(long long)));
         CK(cudaMalloc(&h->dc.q_dev, sizeof(int)));
         CK(cudaMemset(h->dc.q_dev, 0, sizeof(int)));
@@ -1118,6 +1131,7 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
         h->dc.sh = h->sh;
         dk_chol_aat(h->dc, h->stream);
         dk_rebuild(h->dc, h->vc.fix, h->stream);  // lincons.chol = chol_aat (no fixed variables yet)
+        dk_rs_rebuild(h->dc, h->vc.fix, h->stream);
         RET(sync(h));
         if (h->sh->chol_fail) {
             cudaMemsetAsync(&h->sd->chol_fail, 0, sizeof(int), h->stream);
@@ -1493,6 +1507,10 @@ int bnl_get_chol(bnl_handle h, double* L_colmajor, int32_t* dim) {
                 for (int i = 0; i < q; ++i) L_colmajor[(size_t)j * q + i] = (i == j) ? 1.0 : 0.0;
         return BNL_OK;
     }
+    // lincons.chol is only materialised on request: the solve path uses the reduced-space factor (dense.h)
+    dk_rebuild(h->dc, h->vc.fix, h->stream);
+    RET(sync(h));
+    RET(check_chol(h));
     CK(cudaMemcpy(&q, h->dc.q_dev, sizeof(int), cudaMemcpyDeviceToHost));
     const int mpp = h->m_lin + q;
     if (dim) *dim = mpp;
