@@ -467,7 +467,7 @@ def test_native_outer_loop_with_constraints_matches_host_outer_loop():
     S2.use_callbacks(P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons)
     S2.set_params(max_inner_iter=200)
     x_n, y_n, mu, pix = S2.tralcnllss_native(P.x0, max_outer_iter=60)
-    assert rel(x_n, x_h) < 1e-12 and rel(y_n, y_h) < 1e-10 and mu == tr["mu"]
+    assert rel(x_n, x_h) < 1e-12 and rel(y_n, y_h) < 1e-8 and mu == tr["mu"]  # y = y + mu*c amplifies rounding (mu up to 1e9)
     assert np.array_equal(S2.fixvars_words(), tr["fixvars_words"])
     S2.close()
 
