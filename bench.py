@@ -258,7 +258,7 @@ def run_ours(args, cfg):
                            "cg": tr["stats"]["cg_iters"], "breakpoints": tr["stats"]["breakpoints"], "hess_mul": tr["stats"]["hess_mul"],
                            "vthv": tr["stats"]["vthv"], "jtw": tr["stats"]["jtw"], "jac_eval": tr["stats"]["jac_eval"],
                            "chol_rebuilds": tr["stats"]["chol_rebuilds"], "mu": tr["mu"],
-                           "res_eval": tr["stats"]["res_eval"], "allreduces": tr["stats"]["allreduces"],
+                           "res_eval": tr["stats"]["res_eval"], "j_passes": tr["stats"]["j_passes"], "allreduces": tr["stats"]["allreduces"],
                            "p2p_allreduces": tr["stats"]["p2p_allreduces"]},
                 "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"]))},
                 "roofline": {"bound": "hbm", "kernel": "mv_stream_kernel<JTJV> (fused J'(Jv), one pass)", "achieved": achieved,
