@@ -115,6 +115,8 @@ struct bnl_solver {
     // host staging
     double* pin = nullptr;
     size_t pin_doubles = 0;
+    double* pin2[2] = {nullptr, nullptr};  // double-buffered staging for matrix uploads
+    cudaEvent_t pin2_ev[2] = {nullptr, nullptr};
     std::vector<double> h_x, h_y, h_cx, h_cx_next, h_ybar, h_tmp;
 
     // comm
@@ -131,6 +133,7 @@ struct bnl_solver {
     bnl_stats st{};
     std::vector<bnl_inner_record> ilog;
     std::vector<EvPair> ev_busy, ev_free;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // handle-owned pair for whole-call timings (no leak on error paths)
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -441,27 +444,48 @@ int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_o
     return BNL_OK;
 }
 
+// Pageable host memory -> device through TWO pinned staging buffers: the memcpy into one buffer overlaps the async
+// H2D DMA out of the other (cudaMemcpyAsync on the solver's stream, one event per buffer).
+int stage_upload(S* h, const double* src, double* dst, size_t count) {
+    const size_t chunk = (size_t)1 << 19;  // 4 MB per staging buffer
+    if (!h->pin2[0]) {
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaHostAlloc(&h->pin2[b], chunk * sizeof(double), cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&h->pin2_ev[b], cudaEventDisableTiming));
+        }
+    }
+    size_t k = 0;
+    for (size_t off = 0; off < count; off += chunk, ++k) {
+        const int b = (int)(k & 1);
+        const size_t cnt = std::min(chunk, count - off);
+        CK(cudaEventSynchronize(h->pin2_ev[b]));  // the DMA that last read this buffer (this call or an earlier one) is done
+        memcpy(h->pin2[b], src + off, cnt * sizeof(double));
+        CK(cudaMemcpyAsync(dst + off, h->pin2[b], cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(h->pin2_ev[b], h->stream));
+    }
+    return BNL_OK;
+}
+
+// Column-major (Julia) host matrix -> row-major device matrix: staged upload into a temporary column-major device
+// buffer, then one transpose kernel.  Only host-supplied matrices (callback mode, small configs) pay for the temporary.
 int upload_colmajor(S* h, const double* src, long long rows, int cols, long long lds, double* dst_rowmajor, int ldd) {
-    // stage the column-major host matrix through pinned memory into a device column-major buffer, then transpose
-    // only host-supplied matrices (callback mode, small configs) pay for this temporary second buffer
     const size_t total = (size_t)rows * cols;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, std::max<size_t>(total, 1) * sizeof(double)));
-    const size_t chunk = 1 << 20;  // doubles per pinned chunk
-    RET(ensure_pin(h, chunk));
-    for (int c = 0; c < cols; ++c) {
-        for (long long r0 = 0; r0 < rows; r0 += (long long)chunk) {
-            const size_t cnt = (size_t)std::min<long long>(chunk, rows - r0);
-            memcpy(h->pin, src + (size_t)c * lds + r0, cnt * sizeof(double));
-            CK(cudaMemcpyAsync(tmp + (size_t)c * rows + r0, h->pin, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-        }
+    int rc = BNL_OK;
+    if (lds == rows) {
+        rc = stage_upload(h, src, tmp, total);
+    } else {
+        for (int c = 0; c < cols && rc == BNL_OK; ++c) rc = stage_upload(h, src + (size_t)c * lds, tmp + (size_t)c * rows, (size_t)rows);
     }
-    vk_transpose_in(tmp, rows, cols, rows, dst_rowmajor, ldd, h->stream);
-    KLAUNCH();
-    CK(cudaStreamSynchronize(h->stream));
+    if (rc == BNL_OK) {
+        vk_transpose_in(tmp, rows, cols, rows, dst_rowmajor, ldd, h->stream);
+        KLAUNCH();
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = h->fail(BNL_ECUDA, "upload_colmajor: %s", cudaGetErrorString(e));
+    }
     cudaFree(tmp);
-    return BNL_OK;
+    return rc;
 }
 
 // jac_res(x), jac_nlcons(x): fills J (and C in callback mode)
@@ -912,6 +936,8 @@ int bnl_create(int device, bnl_handle* out) {
     }
     cudaMemset(h->sd, 0, sizeof(Scal));
     memset(h->sh, 0, sizeof(Scal));
+    cudaEventCreate(&h->ev_t0);
+    cudaEventCreate(&h->ev_t1);
     *out = h;
     return BNL_OK;
 }
@@ -934,7 +960,13 @@ void bnl_destroy(bnl_handle h) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->pin) cudaFreeHost(h->pin);
+    for (int b = 0; b < 2; ++b) {
+        if (h->pin2[b]) cudaFreeHost(h->pin2[b]);
+        if (h->pin2_ev[b]) cudaEventDestroy(h->pin2_ev[b]);
+    }
     cudaFree(h->sd);
     cudaFreeHost(h->sh);
     cudaStreamDestroy(h->stream);
@@ -1109,6 +1141,7 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
         double* dA = nullptr;
         CK(cudaMalloc(&dA, (size_t)m_lin * ld * sizeof(double)));
         CK(cudaMemset(dA, 0, (size_t)m_lin * ld * sizeof(double)));
+        h->dc.A = dA;  // owned by the handle from here on (freed with the problem even if a later step fails)
         RET(upload_colmajor(h, A, m_lin, n, m_lin, dA, h->ld));
         h->dc.n = n;
         h->dc.ld = h->ld;
@@ -1575,9 +1608,7 @@ int bnl_new_point(bnl_handle h, const double* x, const double* y, double mu, dou
 static int solve_subproblem_host(bnl_handle h, const double* x0, const double* y, double mu, double omega_tol, double* x,
                                  double* cx, double* pix, FILE* log) {
     if (!x0) return BNL_EINVAL;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    cudaEvent_t e0 = h->ev_t0, e1 = h->ev_t1;
     RET(put_vec(h, x0, h->vc.x, h->n));
     CK(cudaEventRecord(e0, h->stream));
     std::vector<double> yv(h->p, 0.0);
@@ -1589,8 +1620,6 @@ static int solve_subproblem_host(bnl_handle h, const double* x0, const double* y
     float t = 0.f;
     cudaEventElapsedTime(&t, e0, e1);
     h->st.solve_ms += t;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (rc != BNL_OK) return rc;
     if (x) RET(get_vec(h, h->vc.x, x, h->n));
     if (cx && h->p > 0) std::copy(h->h_cx.begin(), h->h_cx.end(), cx);
@@ -1646,9 +1675,7 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
     if (kind == 5 && !h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
     const double Jbytes = 8.0 * (double)h->M * (double)h->ld;
     double bytes = 0.0;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    cudaEvent_t e0 = h->ev_t0, e1 = h->ev_t1;
     // the vectors used: x as v (any data), r as w
     for (int rep = -1; rep < reps; ++rep) {  // one untimed warm-up
         if (rep == 0) CK(cudaEventRecord(e0, h->stream));
@@ -1686,8 +1713,6 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
     CK(cudaStreamSynchronize(h->stream));
     float t = 0.f;
     cudaEventElapsedTime(&t, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (avg_ms) *avg_ms = (double)t / reps;
     if (bytes_per_launch) *bytes_per_launch = bytes;
     return BNL_OK;
