@@ -199,6 +199,19 @@ __global__ void __launch_bounds__(kThreads, 1) mv_stream_kernel(const MvArgs a) 
                 }
                 part[q] = (s0 + s1) + (s2 + s3);
             }
+            if constexpr (WARP_TEAM) {
+                // Re-arm the slot as early as provably safe: part[] depends on every J value this lane loaded, the warp
+                // issues in order, and an LDS completes for all lanes at once => once the FMAs producing part[] have
+                // issued, every read of the slot has completed.  The empty asm pins the re-arm below those FMAs.
+                double dep = part[0];
+#pragma unroll
+                for (int q = 1; q < RB; ++q) dep += part[q];
+                asm volatile("" ::"d"(dep) : "memory");
+                if (u == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(j + NSt);
+                }
+            }
             // transposing butterfly: RB values x 32 lanes -> a lane holds one row's warp sum
             double kx;
             if constexpr (RB == 4) {  // 6 shuffles; lane holds row (2*bit4 + bit3)
@@ -229,11 +242,6 @@ __global__ void __launch_bounds__(kThreads, 1) mv_stream_kernel(const MvArgs a) 
             kx += __shfl_xor_sync(0xffffffffu, kx, 1);
             constexpr int LSH = (RB == 4) ? 3 : ((RB == 2) ? 4 : 5);  // row q's sum sits in lanes with (lane >> LSH) == q
             if constexpr (WARP_TEAM) {
-                // the butterfly consumed every lane's partial sums => all reads of the slot have completed
-                if (u == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(j + NSt);
-                }
 #pragma unroll
                 for (int q = 0; q < RB; ++q) t[q] = __shfl_sync(0xffffffffu, kx, q << LSH);
             } else {
