@@ -343,6 +343,7 @@ cudaError_t launch_mode(const MvArgs& a, int kch, int rb, bool warp_team, int gr
     } else {
         if (kch == 4 && rb == 4) BNL_LAUNCH(4, 4, false)
         if (kch == 8 && rb == 2) BNL_LAUNCH(8, 2, false)
+        if (kch == 16 && rb == 1) BNL_LAUNCH(16, 1, false)
     }
     return cudaErrorInvalidValue;
 #undef BNL_LAUNCH
@@ -408,7 +409,7 @@ MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes) {
         while (k2 < kch) k2 <<= 1;
         p.KCH = k2;
         p.RB = (k2 <= 4) ? 4 : (k2 == 8 ? 2 : 1);  // RB*KCH <= 16 double2 of J in registers
-    } else {  // 1024 < ld <= 4096: one 256-thread team
+    } else {  // 1024 < ld <= 8192: one 256-thread team
         p.warp_team = false;
         p.TG = kThreads;
         const int kch = (NC + kThreads - 1) / kThreads;
@@ -418,9 +419,12 @@ MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes) {
         } else if (kch <= 8) {
             p.KCH = 8;
             p.RB = 2;
+        } else if (kch <= 16) {  // 4096 < ld <= 8192: one 64 KB row per stage
+            p.KCH = 16;
+            p.RB = 1;
         } else {
             p.supported = false;
-            return p;  // ld > 4096: outside the streaming kernels' range
+            return p;  // ld > 8192: outside the streaming kernels' range
         }
     }
     p.R = p.RB;  // a stage is one RB-row batch of one team

@@ -12,7 +12,7 @@
 namespace bnl {
 
 constexpr int kP2PMaxRanks = 16;
-constexpr int kP2PWidth = 4096 + 16;  // doubles per mailbox row (ld <= 4096, + the ||Jv||^2 slot)
+constexpr int kP2PWidth = 8192 + 16;  // doubles per mailbox row (ld <= 8192, + the ||Jv||^2 slot)
 
 struct P2PArgs {
     int nranks, rank;

@@ -1089,7 +1089,7 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
     h->mask = (m_lin == 0);
     size_t optin = h->prop.sharedMemPerBlockOptin;
     h->plan = mv_make_plan(M_local, n, h->prop.multiProcessorCount, optin);
-    if (!h->plan.supported) return h->fail(BNL_EDIM, "n = %d unsupported by the streaming kernels (ld <= 4096)", n);
+    if (!h->plan.supported) return h->fail(BNL_EDIM, "n = %d unsupported by the streaming kernels (n <= 8192)", n);
     const size_t ld = h->ld;
     const size_t vlen = ld + kColAlign;  // +16: slot [ld] carries ||Jv||^2
     const int nvec = 17;

@@ -28,7 +28,7 @@ def S():
 # K1-K4: the streaming Jacobian kernels, every tiling regime (TG/G/KCH/RB), ragged M, odd n
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,n", [(4, 3), (1, 1), (33, 5), (1000, 37), (4096, 256), (3001, 250), (2500, 1024), (777, 1000),
-                                 (700, 2048), (300, 4096), (129, 3000), (64, 16), (5000, 64), (200000, 128)])
+                                 (700, 2048), (300, 4096), (129, 3000), (64, 16), (5000, 64), (200000, 128), (90, 8192), (75, 5000)])
 def test_alhessian_matvecs_match_numpy(S, M, n):
     """test/structures.jl:1-16 generalised: H*v, vthv, J*v, J'*w against explicit NumPy (rtol 1e-12)."""
     rng = np.random.default_rng(M * 7919 + n)
@@ -479,7 +479,7 @@ def test_bounds_error_and_dimension_errors(S):
     with pytest.raises(ValueError):
         S.hess_mul(np.zeros(4))  # no Jacobian bound yet
     with pytest.raises(B.DimensionMismatch):
-        S.set_problem(10, 5000)  # n > 4096 is outside the streaming kernels' range
+        S.set_problem(10, 9000)  # n > 8192 is outside the streaming kernels' range
 
 
 # ---------------------------------------------------------------------------------------------------------
