@@ -119,7 +119,7 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.config, "M": cfg["M"], "n": n, "sample_rows": M_s, "model": cfg["model"],
+            "config": {"workload": args.config, "M": cfg["M"], "n": n, "sample_rows": M_s, "residual_family": cfg["model"],
                        "bytes_accounting": "8*M*n per J.v or J'.w product"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,8 +249,8 @@ def run_ours(args, cfg):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.config, "M": M, "n": n, "model": cfg["model"], "rows_per_gpu": M_loc,
-                           "parallelism": f"row-sharded x{world}", "collective": ("fused NVLink peer-memory all-reduce" if S.comm_info()["p2p_allreduce"] else ("nccl" if world > 1 else "none")), "l2": "J shard (>= 10 GB) far exceeds the 126 MB L2",
+                "config": {"workload": args.config, "M": M, "n": n, "residual_family": cfg["model"], "rows_per_gpu": M_loc,
+                           "parallelism": f"row-sharded x{world}", "collective": ("fused NVLink peer-memory all-reduce" if S.comm_info()["p2p_allreduce"] else ("nccl" if world > 1 else "none")), "l2": f"no flush needed: the J shard streamed by every apply is {8.0 * M_loc * n / 1e9:.1f} GB >> 126 MB L2",
                            "bytes_accounting": "8*M*n per J.v or J'.w product; a fused Hessian apply = 2 products, 1 HBM pass",
                            "step": "one full tralcnllss solve to the reference tolerances (defaults)"},
                 "solve_wall_s": t_wall / args.steps, "solve_device_s": dev_ms * 1e-3 / args.steps,

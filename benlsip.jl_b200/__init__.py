@@ -92,8 +92,8 @@ def load_library(build_if_missing: bool = False):
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        if build_if_missing:
-            from . import build as _b  # type: ignore
+        if build_if_missing and os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            from . import build as _b  # type: ignore  (compiles the CUDA sources in-tree; still no CPU substitute)
             _b.build()
         else:
             raise BnlError(f"{LIB_PATH} is missing: run `python benlsip.jl_b200/build.py` (nvcc, sm_100a). "
@@ -170,7 +170,7 @@ class Solver:
     the MixedConstraints state (fixvars + factor), like the pair of mutable structs the reference passes around."""
 
     def __init__(self, device: int = 0):
-        self.lib = load_library()
+        self.lib = load_library(build_if_missing=True)
         self.h = C.c_void_p()
         rc = self.lib.bnl_create(device, C.byref(self.h))
         if rc != 0:

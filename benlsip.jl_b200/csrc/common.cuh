@@ -34,7 +34,6 @@ struct Scal {
     double norm_g, norm_s, pix;
     double sumsq_r;            // dot(rx,rx) (global, after all-reduce)
     double jv_sumsq;           // dot(Jv,Jv) (global)
-    double cdot_yc, cdot_cc;   // dot(y,cx), dot(cx,cx)
     double Cv_sumsq;           // dot(Cv,Cv)
     double c0;                 // built-in nonlinear constraint value c(x) (p = 1)
     int chol_fail;             // device Cholesky hit a non-positive pivot

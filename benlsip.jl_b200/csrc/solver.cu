@@ -117,7 +117,7 @@ struct bnl_solver {
     size_t pin_doubles = 0;
     double* pin2[2] = {nullptr, nullptr};  // double-buffered staging for matrix uploads
     cudaEvent_t pin2_ev[2] = {nullptr, nullptr};
-    std::vector<double> h_x, h_y, h_cx, h_cx_next, h_ybar, h_tmp;
+    std::vector<double> h_x, h_cx, h_cx_next, h_ybar, h_tmp;
 
     // comm
     ncclComm_t comm = nullptr;
@@ -645,7 +645,7 @@ int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool appl
     if (iters_out) *iters_out = nhp;
     if (apply_linesearch_and_accumulate) {
         if (status != BNL_CG_NEGATIVE_CURVATURE) RET(vthv_dev(h, c.w));  // linesearch :775
-        vk_minor_finish(c, 0.0, h->stream);                               // alpha, w *= alpha (:671), s += w (:436)
+        vk_minor_finish(c, h->stream);                                    // alpha, w *= alpha (:671), s += w (:436)
         KLAUNCH();
     }
     return BNL_OK;

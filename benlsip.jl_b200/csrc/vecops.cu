@@ -142,10 +142,6 @@ __global__ void k_norm_to(VecCtx c, const double* v, int which) {
     publish(c.sd, c.sh);
 }
 
-__global__ void k_neg_copy(int n, const double* src, double* dst, int negate) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = negate ? -src[i] : src[i];
-}
-
 // minor_iterate :660-665 (trap T1: finite w_l/w_u on the FIXED variables) + projected_cg prologue :702-718
 template <bool MASK>
 __global__ void k_cg_init(VecCtx c, double delta) {
@@ -595,9 +591,6 @@ void vk_gminor_nrg(const VecCtx& c, bool mask, cudaStream_t st) {
         k_gminor_nrg<false><<<1, kVT, 0, st>>>(c);
 }
 void vk_norm_to(const VecCtx& c, const double* v, int which, cudaStream_t st) { k_norm_to<<<1, kVT, 0, st>>>(c, v, which); }
-void vk_neg_copy(const VecCtx& c, const double* src, double* dst, bool negate, cudaStream_t st) {
-    k_neg_copy<<<1, kVT, 0, st>>>(c.n, src, dst, negate ? 1 : 0);
-}
 void vk_cg_init(const VecCtx& c, bool mask, double delta, cudaStream_t st) {
     if (mask)
         k_cg_init<true><<<1, kVT, 0, st>>>(c, delta);
@@ -612,7 +605,7 @@ void vk_cg_step(const VecCtx& c, bool mask, int phase, cudaStream_t st) {
     else
         k_cg_step<false, 1><<<1, kVT, 0, st>>>(c);
 }
-void vk_minor_finish(const VecCtx& c, double, cudaStream_t st) { k_minor_finish<<<1, kVT, 0, st>>>(c); }
+void vk_minor_finish(const VecCtx& c, cudaStream_t st) { k_minor_finish<<<1, kVT, 0, st>>>(c); }
 void vk_minor_post(const VecCtx& c, bool mask, double delta, cudaStream_t st) {
     if (mask)
         k_minor_post<true><<<1, kVT, 0, st>>>(c, delta);

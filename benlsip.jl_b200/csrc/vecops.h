@@ -27,10 +27,9 @@ void vk_cauchy_eval(const VecCtx& c, double delta, cudaStream_t st);            
 void vk_cauchy_advance(const VecCtx& c, bool mask, int breakpoint, cudaStream_t st);
 void vk_gminor_nrg(const VecCtx& c, bool mask, cudaStream_t st);                  // gm = hv + g; nrg_g, nrg_gm [mask]
 void vk_norm_to(const VecCtx& c, const double* v, int which, cudaStream_t st);    // which: 0 nrg_g, 1 nrg_gm, 2 pix, 3 norm_g, 4 norm_s
-void vk_neg_copy(const VecCtx& c, const double* src, double* dst, bool negate, cudaStream_t st);
 void vk_cg_init(const VecCtx& c, bool mask, double delta, cudaStream_t st);
 void vk_cg_step(const VecCtx& c, bool mask, int phase, cudaStream_t st);          // phase 0: all (mask) / a ; 1: b (general)
-void vk_minor_finish(const VecCtx& c, double mu_Cw_sumsq_scale, cudaStream_t st); // linesearch + w *= alpha + s += w
+void vk_minor_finish(const VecCtx& c, cudaStream_t st);                           // linesearch + w *= alpha + s += w
 void vk_minor_post(const VecCtx& c, bool mask, double delta, cudaStream_t st);    // gm = hv+g; active_bounds; add_active; nrg
 void vk_dot_gs(const VecCtx& c, cudaStream_t st);                                 // gs = g.s
 void vk_trial_point(const VecCtx& c, cudaStream_t st);                            // xn = x + s; norm_s
