@@ -508,3 +508,13 @@ def test_full_size_properties(S):
     e[5] = 1.0
     d = S.hess_mul(e)[5]
     assert abs(d / (1.21 * M / (3 * n)) - 1.0) < 5e-3
+    # the last 1000 rows of the full-size device problem against the oracle's definition of the same rows
+    tail = 1000
+    P = GlmProblem(tail, n, seed=3, row0=M - tail)
+    x = x0 + 0.05 * np.cos(np.arange(n))
+    S.eval_jacobian(x)
+    r_dev, _ = S.residuals(x)
+    assert np.max(np.abs(r_dev[-tail:] - P.residuals(x))) < 1e-13
+    J_tail = P.jac_res(x)
+    assert np.max(np.abs(S.jv(e)[-tail:] - J_tail[:, 5])) < 1e-15
+    assert rel(S.jv(v)[-tail:], J_tail @ v) < 1e-12
