@@ -121,6 +121,7 @@ def load_library(build_if_missing: bool = False):
         "bnl_vthv": ([H, _DP, _DP], C.c_int), "bnl_jv": ([H, _DP, _DP], C.c_int), "bnl_jtw": ([H, _DP, _DP], C.c_int),
         "bnl_gram": ([H, _DP, _DP], C.c_int), "bnl_set_hessian_mode": ([H, i32], C.c_int), "bnl_project": ([H, _DP, _DP], C.c_int),
         "bnl_active_bounds_reset": ([H, _DP], C.c_int),
+        "bnl_left_mul": ([H, _DP, _DP], C.c_int), "bnl_left_mul_tr": ([H, _DP, _DP], C.c_int),
         "bnl_active_bounds": ([H, _DP, _DP, dbl, C.POINTER(i64), C.POINTER(i32)], C.c_int),
         "bnl_add_active": ([H, C.POINTER(i64), i32], C.c_int),
         "bnl_set_fixvars": ([H, C.POINTER(C.c_uint64)], C.c_int),
@@ -356,6 +357,19 @@ class Solver:
         """`projection(lincons, r)` (src/polyhedral_constraints.jl:150-170)."""
         out = np.empty(self.n)
         self._ck(self.lib.bnl_project(self.h, _p(_vec(r, self.n)), _p(out)))
+        return out
+
+    def left_mul(self, x):
+        """`left_mul(lincons, x)` = [A x; x[fix]] (src/polyhedral_constraints.jl:86-98)."""
+        out = np.empty(self.m_lin + self.nb_fix())
+        self._ck(self.lib.bnl_left_mul(self.h, _p(_vec(x, self.n)), _p(out)))
+        return out
+
+    def left_mul_tr(self, y):
+        """`left_mul_tr(lincons, y)` = A~' y (src/polyhedral_constraints.jl:72-84)."""
+        yv = _vec(y, self.m_lin + self.nb_fix())
+        out = np.empty(self.n)
+        self._ck(self.lib.bnl_left_mul_tr(self.h, _p(yv), _p(out)))
         return out
 
     def active_bounds_reset(self, x):

@@ -171,6 +171,28 @@ __global__ void k_project(DenseCtx c, const double* r, double* v, int negate) {
     for (int j = threadIdx.x; j < c.n; j += blockDim.x) v[j] = sgn * r[j] - v[j];
 }
 
+__global__ void k_left_mul(DenseCtx c, const double* x, double* y) {
+    const int m = c.m, q = *c.q_dev;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < m; i += nw) {
+        double s = 0.0;
+        for (int j = lane; j < c.n; j += 32) s = fma(c.A[(size_t)i * c.ld + j], x[j], s);
+        s = warp_sum(s);
+        if (lane == 0) y[i] = s;
+    }
+    for (int k = threadIdx.x; k < q; k += blockDim.x) y[m + k] = x[c.fixidx[k]];
+}
+__global__ void k_left_mul_tr(DenseCtx c, const double* y, double* x) {
+    const int m = c.m, q = *c.q_dev;
+    for (int j = threadIdx.x; j < c.n; j += blockDim.x) {
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) s = fma(c.A[(size_t)i * c.ld + j], y[i], s);
+        x[j] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < q; k += blockDim.x) x[c.fixidx[k]] += y[m + k];
+}
+
 // ---- reduced-space projection --------------------------------------------------------------------------------
 // Lr = cholesky(A_free A_free').L   (m x m, column-major, global memory; factorisation by warp 0)
 __global__ void k_rs_rebuild(DenseCtx c, const unsigned char* fix) {
@@ -263,6 +285,8 @@ __global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double*
 
 }  // namespace
 
+void dk_left_mul(const DenseCtx& c, const double* x, double* y, cudaStream_t st) { k_left_mul<<<1, kDT, 0, st>>>(c, x, y); }
+void dk_left_mul_tr(const DenseCtx& c, const double* y, double* x, cudaStream_t st) { k_left_mul_tr<<<1, kDT, 0, st>>>(c, y, x); }
 void dk_rs_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st) { k_rs_rebuild<<<1, kDT, 0, st>>>(c, fix); }
 void dk_rs_project(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, bool negate, cudaStream_t st) {
     k_rs_project<<<1, kDT, 0, st>>>(c, fix, r, v, negate ? 1 : 0);

@@ -26,6 +26,10 @@ void dk_chol_aat(const DenseCtx& c, cudaStream_t st);                           
 void dk_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st);     // update_chol!  :62-68
 void dk_project(const DenseCtx& c, const double* r, double* v, bool negate, cudaStream_t st);  // projection! :158-170
 
+// left_mul (A~ x = [A x; x[fix]], :86-98) and left_mul_tr (A~' y, :72-84) on their own (the reference's tests call them)
+void dk_left_mul(const DenseCtx& c, const double* x, double* y, cudaStream_t st);      // y: m + q (needs dk_rebuild's fixidx)
+void dk_left_mul_tr(const DenseCtx& c, const double* y, double* x, cudaStream_t st);   // x: n
+
 // Reduced-space form of the same projection (default on the solve path).  A~A~' = [AA' A_F; A_F' I] and
 // S = I - G'G is a rank-m downdate of the identity, so P(r) = r - A~'(A~A~')^{-1}A~ r is equivalently
 //     v_F = 0,   v_free = r_free - A_free' (A_free A_free')^{-1} A_free r_free

@@ -1452,6 +1452,48 @@ int bnl_project(bnl_handle h, const double* r, double* v) {
     return BNL_OK;
 }
 
+// left_mul(lincons, x) -> y (length m_lin + nb_fix)  and  left_mul_tr(lincons, y) -> x   (src/polyhedral_constraints.jl:72-98)
+static int left_mul_common(bnl_handle h, const double* in, double* out, bool transpose) {
+    if (!in || !out) return BNL_EINVAL;
+    int q = 0;
+    RET(bnl_get_fixvars(h, nullptr, &q));
+    const int mpp = h->m_lin + q;
+    std::vector<double> host(std::max(h->n, mpp), 0.0);
+    if (h->mask) {  // no linear equalities: A~ = rows of the identity
+        std::vector<uint64_t> words((h->n + 63) / 64);
+        RET(bnl_get_fixvars(h, words.data(), &q));
+        int k = 0;
+        if (!transpose) {
+            for (int i = 0; i < h->n; ++i)
+                if ((words[i >> 6] >> (i & 63)) & 1ull) out[k++] = in[i];
+        } else {
+            for (int i = 0; i < h->n; ++i) out[i] = ((words[i >> 6] >> (i & 63)) & 1ull) ? in[k++] : 0.0;
+        }
+        return BNL_OK;
+    }
+    dk_rebuild(h->dc, h->vc.fix, h->stream);  // refresh the ascending index list of fixed variables
+    if (!transpose) {
+        RET(put_vec(h, in, h->vc.t2, h->n));
+        dk_left_mul(h->dc, h->vc.t2, h->dc.ywork, h->stream);
+        RET(sync(h));
+        RET(get_vec(h, h->dc.ywork, out, mpp));
+    } else {
+        RET(put_vec(h, in, h->dc.ywork, mpp));
+        dk_left_mul_tr(h->dc, h->dc.ywork, h->vc.t2, h->stream);
+        RET(sync(h));
+        RET(get_vec(h, h->vc.t2, out, h->n));
+    }
+    return BNL_OK;
+}
+int bnl_left_mul(bnl_handle h, const double* x, double* y) {
+    ENTER();
+    return left_mul_common(h, x, y, false);
+}
+int bnl_left_mul_tr(bnl_handle h, const double* y, double* x) {
+    ENTER();
+    return left_mul_common(h, y, x, true);
+}
+
 int bnl_active_bounds_reset(bnl_handle h, const double* x) {
     ENTER();
     RET(put_vec(h, x, h->vc.t2, h->n));

@@ -157,6 +157,8 @@ int bnl_set_hessian_mode(bnl_handle h, int32_t mode);
 
 /* ---- MixedConstraints methods (src/polyhedral_constraints.jl) --------------------------------------- */
 int bnl_project(bnl_handle h, const double* r, double* v);                 /* projection!          :158-170 */
+int bnl_left_mul(bnl_handle h, const double* x, double* y);                /* left_mul: y = [A x; x[fix]]  :86-98 (y: m_lin + nb_fix) */
+int bnl_left_mul_tr(bnl_handle h, const double* y, double* x);             /* left_mul_tr: x = A~' y       :72-84 */
 int bnl_active_bounds_reset(bnl_handle h, const double* x);                /* active_bounds!       :203-215 */
 int bnl_active_bounds(bnl_handle h, const double* x, const double* s, double delta, int64_t* idx,
                       int32_t* count);                                     /* active_bounds        :219-237 */

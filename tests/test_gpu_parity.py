@@ -127,6 +127,10 @@ def test_hs48_projection_golden_vector(S):
     x_hs = np.array([3.0, 5, -3, 2, -2])
     S.set_problem(1, 5, A)
     S.set_fixvars([True, True, False, False, False])
+    Bm = np.vstack([A, np.eye(5)[[0, 1], :]])
+    yv = np.array([0.3, -0.7, 1.1, 0.25])
+    np.testing.assert_allclose(S.left_mul_tr(yv), Bm.T @ yv, rtol=1e-14)  # test/structures.jl:49
+    np.testing.assert_allclose(S.left_mul(x_hs), Bm @ x_hs, rtol=1e-14)   # test/structures.jl:50
     proj = S.projection(x_hs)
     np.testing.assert_allclose(proj, [0.0, 0, 0, 2, -2], rtol=0, atol=1e-14)
     v = A @ proj
