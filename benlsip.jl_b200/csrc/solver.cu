@@ -165,8 +165,8 @@ namespace {
 typedef bnl_solver S;
 
 int sync(S* h) {
+    if (h->p2p_on) vk_publish(h->sd, h->sh, h->stream);  // make a peer-wait timeout visible even when no O(n) kernel followed
     CK(cudaStreamSynchronize(h->stream));
-    // (the O(n) kernel that follows every all-reduce publishes the scalars, p2p_timeout included)
     if (h->p2p_on && h->sh->p2p_timeout) return h->fail(BNL_ENCCL, "peer-memory all-reduce timed out waiting for a rank");
     // harvest finished event pairs
     for (size_t i = 0; i < h->ev_busy.size();) {
