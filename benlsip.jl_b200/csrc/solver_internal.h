@@ -1,0 +1,198 @@
+// solver_internal.h -- state and internal interface of the host-side solver (shared by solver.cu, the control flow,
+// and capi.cu, the extern "C" layer).  Not installed: the public interface is include/benlsip_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/benlsip_b200.h"
+#include "common.cuh"
+#include "dense.h"
+#include "gram.h"
+#include "matvec.h"
+#include "models.h"
+#include "p2p.h"
+#include "vecops.h"
+
+
+using namespace bnl;
+
+
+// ---- NCCL through dlopen: no link-time dependency; a single-GPU user never loads it ---------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+extern NcclApi g_nccl;
+
+constexpr double kInf = std::numeric_limits<double>::infinity();
+
+
+struct EvPair {
+    cudaEvent_t a, b;
+    int cls;
+};
+
+struct bnl_solver {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+    bnl_params prm{};
+    bool problem_set = false;
+
+    long long M = 0, M_total = 0, row0 = 0;
+    int n = 0, ld = 0, m_lin = 0, p = 0;
+    bool mask = true;
+    bool literal_proj = false;  // BNL_LITERAL_PROJECTION=1: the reference's block factor on the solve path too
+
+    double *J = nullptr, *r = nullptr, *r_trial = nullptr, *ydata = nullptr, *tvec = nullptr;
+    double* vecpool = nullptr;
+    unsigned char* flagpool = nullptr;
+    VecCtx vc{};
+    DenseCtx dc{};
+    double* partial = nullptr;
+    double* sumsq_partial = nullptr;
+    int sumsq_blocks = 148 * 8;
+    unsigned long long* d_words = nullptr;
+    long long* d_idx = nullptr;
+    int* d_count = nullptr;
+    Scal *sd = nullptr, *sh = nullptr;
+    MvPlan plan{};
+    double* gram = nullptr;     // G = J'J (ld x ld), all-reduced
+    double* gram_ws = nullptr;  // split-K workspace
+    int gram_nsplit = 0;
+    int hess_mode = 0;          // BNL_HESSIAN_MATRIX_FREE / BNL_HESSIAN_GRAM
+    bool gram_valid = false;
+
+    // model binding
+    int model_id = 0;
+    uint32_t seed = 0;
+    double noise = 0.0, cond_exp = 0.0;
+    double* d_cs = nullptr;
+    double* d_xtrue = nullptr;
+    std::vector<double> m_x0, m_xlow, m_xupp, m_xtrue;
+    bnl_callback cb_res = nullptr, cb_jac = nullptr, cb_nl = nullptr, cb_jnl = nullptr;
+    void* cb_ctx = nullptr;
+    bool have_J = false;
+    int nl_kind = 0;       // built-in nonlinear constraint (BNL_NLCONS_*), 0 = none / callbacks
+    double nl_rho2 = 0.0;
+
+    // host staging
+    double* pin = nullptr;
+    size_t pin_doubles = 0;
+    double* pin2[2] = {nullptr, nullptr};  // double-buffered staging for matrix uploads
+    cudaEvent_t pin2_ev[2] = {nullptr, nullptr};
+    std::vector<double> h_x, h_cx, h_cx_next, h_ybar, h_tmp;
+
+    // comm
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    // peer-memory all-reduce (p2p.h)
+    bool p2p_on = false;
+    P2PArgs p2p{};
+    double* p2p_buf = nullptr;
+    unsigned int* p2p_counter = nullptr;
+    unsigned long long p2p_epoch = 0;
+    void* p2p_opened[kP2PMaxRanks] = {nullptr};
+
+    bnl_stats st{};
+    std::vector<bnl_inner_record> ilog;
+    std::vector<EvPair> ev_busy, ev_free;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // handle-owned pair for whole-call timings (no leak on error paths)
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return h->fail(e_ == cudaErrorMemoryAllocation ? BNL_EOOM : BNL_ECUDA, "%s:%d %s: %s", __FILE__, \
+                           __LINE__, #call, cudaGetErrorString(e_));                                         \
+    } while (0)
+#define RET(call)                  \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != BNL_OK) return rc_; \
+    } while (0)
+#define KLAUNCH() (h->st.kernel_launches++)
+
+
+namespace bnl_host {
+
+typedef bnl_solver S;
+
+struct EvScope {  // records a CUDA-event pair around a kernel class on the launching stream
+    S* h;
+    EvPair e{};
+    bool ok = false;
+    EvScope(S* h_, int cls);
+    ~EvScope();
+};
+
+int sync(S* h);
+int ensure_pin(S* h, size_t doubles);
+int put_vec(S* h, const double* src, double* dst, size_t count);
+int get_vec(S* h, const double* src_dev, double* dst, size_t count);
+int allreduce(S* h, double* buf, size_t count);
+int form_gram(S* h);
+int hess_mul(S* h, const double* dv, double* out);
+int vthv_dev(S* h, const double* dv);
+int jtw_dev(S* h, const double* dw, double* out);
+int rebuild_chol(S* h);
+int check_chol(S* h);
+int project_general(S* h, const double* src, double* dst, bool negate);
+bnl::ModelArgs margs(S* h);
+int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_out);
+int upload_colmajor(S* h, const double* src, long long rows, int cols, long long lds, double* dst_rowmajor, int ldd);
+int eval_jacobian(S* h, const double* dx);
+int gradient(S* h, const double* rbuf, const std::vector<double>& ybar);
+int cauchy_step(S* h, double delta);
+int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool apply_linesearch_and_accumulate);
+int inner_step(S* h, double delta, double* pred_out);
+int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out);
+int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double omega_tol, double* pix_out, FILE* log);
+int free_problem(S* h);
+void sync_params_to_ctx(S* h);
+inline bool valid(S* h) { return h != nullptr; }
+
+}  // namespace bnl_host
