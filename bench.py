@@ -234,6 +234,22 @@ def run_ours(args, cfg):
                       "x_rel_diff_vs_matrix_free": float(np.linalg.norm(xg - x) / np.linalg.norm(x)),
                       "matvec_equiv_GBps": 8.0 * M * n * (stg["jv"] + stg["jtw"]) / tg / 1e9}
         S.set_hessian_mode(B.HESSIAN_MATRIX_FREE)
+    # extra: one solve with the opt-in incremental Cauchy search (no Hessian apply per breakpoint)
+    inc_extra = None
+    if args.hessian == "matrix_free" and not args.no_gram_extra and cfg["model"] != "glm_mixed":
+        S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+        step()
+        barrier()
+        ti0 = time.perf_counter()
+        xi, tri, _ = step()
+        barrier()
+        ti = time.perf_counter() - ti0
+        sti = tri["stats"]
+        inc_extra = {"solve_wall_s": ti, "outer": tri["outer_iters"], "inner": sti["inner_iters"], "breakpoints": sti["breakpoints"],
+                     "hess_mul": sti["hess_mul"], "j_passes": sti["j_passes"],
+                     "x_rel_diff_vs_default": float(np.linalg.norm(xi - x) / np.linalg.norm(x)),
+                     "matvec_equiv_GBps_literal_accounting": 8.0 * M * n * (st["jv"] + st["jtw"]) / ti / 1e9}
+        S.set_cauchy_mode(B.CAUCHY_LITERAL)
     # max over ranks of both clocks
     if world > 1:
         tt = torch.tensor([t_wall, dev_ms], dtype=torch.float64, device="cuda")
@@ -278,6 +294,8 @@ def run_ours(args, cfg):
             line["roofline"]["traffic_source"] = tj["source"]
         if gram_extra is not None:
             line["gram_mode"] = gram_extra
+        if inc_extra is not None:
+            line["incremental_cauchy_mode"] = inc_extra
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, cfg)
         print(json.dumps(line), flush=True)

@@ -29,6 +29,7 @@ CG_SOLVED, CG_BOUND_HIT, CG_NEGATIVE_CURVATURE, CG_MAX_ITER, CG_NOTHING = 0, 1, 
 MODEL_GLM, MODEL_EXPSUM = 1, 2
 HESSIAN_MATRIX_FREE, HESSIAN_GRAM = 0, 1
 NLCONS_SPHERE = 1
+CAUCHY_LITERAL, CAUCHY_INCREMENTAL = 0, 1
 
 
 class BnlError(RuntimeError):
@@ -69,7 +70,7 @@ class Stats(C.Structure):
                                           "vthv", "jtw", "jv", "res_eval", "jac_eval", "chol_rebuilds", "allreduces")] + \
                [(k, C.c_double) for k in ("hess_mul_ms", "vthv_ms", "jtw_ms", "res_eval_ms", "jac_eval_ms", "solve_ms")] + \
                [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double),
-                ("p2p_allreduces", C.c_int64)]
+                ("p2p_allreduces", C.c_int64), ("inc_breakpoints", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -119,7 +120,7 @@ def load_library(build_if_missing: bool = False):
         "bnl_set_mu": ([H, dbl], C.c_int), "bnl_eval_jacobian": ([H, _DP], C.c_int),
         "bnl_residuals": ([H, _DP, _DP, _DP], C.c_int), "bnl_hess_mul": ([H, _DP, _DP], C.c_int),
         "bnl_vthv": ([H, _DP, _DP], C.c_int), "bnl_jv": ([H, _DP, _DP], C.c_int), "bnl_jtw": ([H, _DP, _DP], C.c_int),
-        "bnl_gram": ([H, _DP, _DP], C.c_int), "bnl_set_hessian_mode": ([H, i32], C.c_int), "bnl_project": ([H, _DP, _DP], C.c_int),
+        "bnl_gram": ([H, _DP, _DP], C.c_int), "bnl_set_hessian_mode": ([H, i32], C.c_int), "bnl_set_cauchy_mode": ([H, i32], C.c_int), "bnl_project": ([H, _DP, _DP], C.c_int),
         "bnl_active_bounds_reset": ([H, _DP], C.c_int),
         "bnl_left_mul": ([H, _DP, _DP], C.c_int), "bnl_left_mul_tr": ([H, _DP, _DP], C.c_int),
         "bnl_active_bounds": ([H, _DP, _DP, dbl, C.POINTER(i64), C.POINTER(i32)], C.c_int),
@@ -347,6 +348,10 @@ class Solver:
         ms = C.c_double()
         self._ck(self.lib.bnl_gram(self.h, _p(G), C.byref(ms)))
         return G, ms.value
+
+    def set_cauchy_mode(self, mode):
+        """CAUCHY_LITERAL (reference: a Hessian apply per breakpoint, default) or CAUCHY_INCREMENTAL (bound-only problems)."""
+        self._ck(self.lib.bnl_set_cauchy_mode(self.h, int(mode)))
 
     def set_hessian_mode(self, mode):
         """HESSIAN_MATRIX_FREE (reference semantics, default) or HESSIAN_GRAM (G = J'J on the FP64 tensor cores)."""

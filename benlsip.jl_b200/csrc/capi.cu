@@ -578,6 +578,12 @@ int bnl_gram(bnl_handle h, double* G_colmajor, double* ms) {
     return BNL_OK;
 }
 
+int bnl_set_cauchy_mode(bnl_handle h, int32_t mode) {
+    if (!valid(h) || (mode != BNL_CAUCHY_LITERAL && mode != BNL_CAUCHY_INCREMENTAL)) return BNL_EINVAL;
+    h->cauchy_mode = mode;
+    return BNL_OK;
+}
+
 int bnl_set_hessian_mode(bnl_handle h, int32_t mode) {
     if (!valid(h) || (mode != BNL_HESSIAN_MATRIX_FREE && mode != BNL_HESSIAN_GRAM)) return BNL_EINVAL;
     h->hess_mode = mode;

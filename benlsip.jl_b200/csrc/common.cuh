@@ -20,6 +20,7 @@ struct Scal {
     // cauchy_step
     double phi_p, phi_pp, theta;
     long long bp_ind;
+    double bp_dind;            // d[bp_ind] at the time of the scan (incremental Cauchy mode)
     // projected_cg
     double pHp, rtv, alpha, gamma, beta, tol_cg;
     int cg_neg_curv, cg_outside, cg_solved, cg_iter;

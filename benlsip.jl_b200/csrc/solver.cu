@@ -389,6 +389,63 @@ double al_value(S* h, double sumsq, const std::vector<double>& y, const std::vec
     return 0.5 * sumsq + yc + 0.5 * mu * cc;
 }
 
+// ---- cauchy_step :574-639, incremental form (opt-in, bound-only problems) -----------------------------------------
+// Same search, same decisions; the two scalars it needs per interval are maintained from t = J d and u = J s_c instead
+// of a fresh Hd = H*d per breakpoint (:633): one strided column of J + two M-vector streams instead of a pass over J.
+int cauchy_step_incremental(S* h, double delta) {
+    VecCtx& c = h->vc;
+    if (!h->inc_t) {
+        const size_t mb = std::max<size_t>(h->M, 16) * sizeof(double);
+        CK(cudaMalloc(&h->inc_t, mb));
+        CK(cudaMalloc(&h->inc_u, mb));
+        CK(cudaMalloc(&h->inc_partial, 2 * (size_t)h->inc_blocks * sizeof(double)));
+        CK(cudaMalloc(&h->inc_out2, 16 * sizeof(double)));
+    }
+    vk_active_reset(c, c.x, nullptr, h->stream);  // :591
+    vk_cauchy_init(c, true, h->stream);           // s_c = 0 ; d = P(-g) :592
+    h->st.kernel_launches += 2;
+    {   // t = J d  (one J pass; ||t||^2 is recomputed below together with u.t = 0)
+        EvScope ev(h, 1);
+        CK(mv_launch(MODE_JV, h->plan, h->J, h->M, c.d, nullptr, h->inc_t, h->partial, c.hv, h->stream));
+    }
+    h->st.kernel_launches += 2;
+    h->st.j_passes += 1;
+    h->st.jv++;
+    auto scalars = [&](int first) -> int {
+        vk_cauchy_inc(c, h->J, h->M, h->inc_t, h->inc_u, h->inc_partial, h->inc_blocks, first, h->stream);
+        vk_cauchy_inc_reduce(h->inc_partial, h->inc_blocks, h->inc_out2, h->stream);
+        h->st.kernel_launches += 2;
+        RET(allreduce(h, h->inc_out2, 2));
+        vk_cauchy_eval_inc(c, delta, h->inc_out2, h->stream);
+        KLAUNCH();
+        return sync(h);
+    };
+    RET(scalars(1));
+    bool min_found = false;
+    const int nmm = h->n - h->m_lin;
+    while (!min_found && h->sh->nb_fix < nmm) {  // :615
+        const double phi_p = h->sh->phi_p, phi_pp = h->sh->phi_pp, theta = h->sh->theta;
+        const double delta_t = (phi_pp > 0) ? -phi_p / phi_pp : 0.0;
+        if (phi_p >= 0) {
+            min_found = true;
+        } else if (phi_p < 0 && phi_pp > 0 && delta_t < theta) {
+            vk_cauchy_advance(c, true, 0, h->stream);
+            KLAUNCH();
+            min_found = true;
+        } else {
+            if (h->sh->bp_ind < 0) return h->fail(BNL_EBOUNDS, "BoundsError: next_breakpoint found no breakpoint (ind = -1)");
+            // the M-vector update reads theta / ind / d[ind] of THIS scan from the device scalars, so it must be queued
+            // before the advance kernel overwrites nothing it needs (advance only touches s, fix, d, nb_fix)
+            vk_cauchy_advance(c, true, 1, h->stream);
+            KLAUNCH();
+            RET(scalars(0));
+            h->st.breakpoints++;
+            h->st.inc_breakpoints++;
+        }
+    }
+    return BNL_OK;
+}
+
 // ---- cauchy_step :574-639 --------------------------------------------------------------------------------
 int cauchy_step(S* h, double delta) {
     VecCtx& c = h->vc;
@@ -496,7 +553,10 @@ int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool appl
 // ---- inner_step :394-460 ---------------------------------------------------------------------------------
 int inner_step(S* h, double delta, double* pred_out) {
     VecCtx& c = h->vc;
-    RET(cauchy_step(h, delta));       // :410
+    if (h->cauchy_mode == BNL_CAUCHY_INCREMENTAL && h->mask)
+        RET(cauchy_step_incremental(h, delta));
+    else
+        RET(cauchy_step(h, delta));  // :410
     RET(hess_mul(h, c.s, c.hv));      // g_minor = H*s+g :412
     vk_gminor_nrg(c, h->mask, h->stream);
     KLAUNCH();
@@ -657,6 +717,11 @@ int free_problem(S* h) {
     cudaFree(h->d_xtrue);
     cudaFree(h->gram);
     cudaFree(h->gram_ws);
+    cudaFree(h->inc_t);
+    cudaFree(h->inc_u);
+    cudaFree(h->inc_partial);
+    cudaFree(h->inc_out2);
+    h->inc_t = h->inc_u = h->inc_partial = h->inc_out2 = nullptr;
     h->gram_ws = nullptr;
     h->gram_valid = false;
     cudaFree(h->vc.C);

@@ -94,6 +94,9 @@ struct bnl_solver {
     int gram_nsplit = 0;
     int hess_mode = 0;          // BNL_HESSIAN_MATRIX_FREE / BNL_HESSIAN_GRAM
     bool gram_valid = false;
+    int cauchy_mode = 0;        // BNL_CAUCHY_LITERAL / BNL_CAUCHY_INCREMENTAL
+    double *inc_t = nullptr, *inc_u = nullptr, *inc_partial = nullptr, *inc_out2 = nullptr;
+    int inc_blocks = 148 * 8;
 
     // model binding
     int model_id = 0;

@@ -77,8 +77,90 @@ __global__ void k_cauchy_eval(VecCtx c, double delta) {
         c.sd->phi_pp = e;
         c.sd->theta = th;
         c.sd->bp_ind = ind;
+        c.sd->bp_dind = (ind >= 0) ? c.d[ind] : 0.0;
     }
     publish(c.sd, c.sh);
+}
+
+// Incremental form: phi' = u.t + g.d, phi'' = ||t||^2 come from the M-vector kernel (out2 = [tt, ut], all-reduced).
+__global__ void k_cauchy_eval_inc(VecCtx c, double delta, const double* __restrict__ out2) {
+    __shared__ double shd[32];
+    __shared__ long long shl[32];
+    double b = 0.0;
+    double th = INFINITY;
+    long long ind = -1;
+    for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
+        const double di = c.d[i], si = c.s[i];
+        b = fma(c.g[i], di, b);
+        if (!c.fix[i]) {
+            double tt = INFINITY;
+            if (di < 0.0) {
+                const double dl = fmax(c.xlow[i] - c.x[i], -delta);
+                tt = (dl - si) / di;
+            } else if (di > 0.0) {
+                const double du = fmin(c.xupp[i] - c.x[i], delta);
+                tt = (du - si) / di;
+            }
+            if (tt < th) {
+                th = tt;
+                ind = i;
+            }
+        }
+    }
+    b = block_sum(b, shd);
+    block_argmin(th, ind, shd, shl);
+    if (threadIdx.x == 0) {
+        c.sd->phi_p = out2[1] + b;  // dot(s_c,Hd) = (J s_c).(J d)
+        c.sd->phi_pp = out2[0];     // dot(d,Hd)   = ||J d||^2
+        c.sd->theta = th;
+        c.sd->bp_ind = ind;
+        c.sd->bp_dind = (ind >= 0) ? c.d[ind] : 0.0;
+    }
+    publish(c.sd, c.sh);
+}
+
+// Local rows: (first == 0) u += theta*t ; t -= d_ind*J[:,ind] ;  partial2[cta] = {sum t^2, sum u*t}.  theta, ind, d_ind are
+// read from the device scalars of the scan that chose this breakpoint.  first == 1: u = 0, only the sums (t = J d just computed).
+__global__ void __launch_bounds__(256) k_cauchy_inc(VecCtx c, const double* __restrict__ J, long long M, double* __restrict__ t,
+                                                    double* __restrict__ u, double* __restrict__ partial2, int first) {
+    __shared__ double shd[32];
+    const double theta = c.sd->theta, dind = c.sd->bp_dind;
+    const long long ind = c.sd->bp_ind;
+    double tt = 0.0, ut = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+        double ti = t[i], ui;
+        if (first) {
+            ui = 0.0;
+        } else {
+            ui = fma(theta, ti, u[i]);
+            ti = fma(-dind, __ldg(J + (size_t)i * c.ld + ind), ti);
+            t[i] = ti;
+        }
+        u[i] = ui;
+        tt = fma(ti, ti, tt);
+        ut = fma(ui, ti, ut);
+    }
+    tt = block_sum(tt, shd);
+    ut = block_sum(ut, shd);
+    if (threadIdx.x == 0) {
+        partial2[2 * blockIdx.x] = tt;
+        partial2[2 * blockIdx.x + 1] = ut;
+    }
+}
+__global__ void k_cauchy_inc_reduce(const double* __restrict__ partial2, int nblocks, double* __restrict__ out2) {
+    __shared__ double shd[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+        a += partial2[2 * i];
+        b += partial2[2 * i + 1];
+    }
+    a = block_sum(a, shd);
+    b = block_sum(b, shd);
+    if (threadIdx.x == 0) {
+        out2[0] = a;
+        out2[1] = b;
+    }
 }
 
 // :622-635.  breakpoint == 0: s_c += (-phi_p/phi_pp) d.   breakpoint == 1: s_c += theta d; add_active!(ind); d = P(-g)
@@ -578,6 +660,16 @@ void vk_cauchy_init(const VecCtx& c, bool mask, cudaStream_t st) {
         k_cauchy_init<false><<<1, kVT, 0, st>>>(c);
 }
 void vk_cauchy_eval(const VecCtx& c, double delta, cudaStream_t st) { k_cauchy_eval<<<1, kVT, 0, st>>>(c, delta); }
+void vk_cauchy_inc(const VecCtx& c, const double* J, long long M, double* t, double* u, double* partial2, int nblocks, int first,
+                   cudaStream_t st) {
+    k_cauchy_inc<<<nblocks, 256, 0, st>>>(c, J, M, t, u, partial2, first);
+}
+void vk_cauchy_inc_reduce(const double* partial2, int nblocks, double* out2, cudaStream_t st) {
+    k_cauchy_inc_reduce<<<1, 256, 0, st>>>(partial2, nblocks, out2);
+}
+void vk_cauchy_eval_inc(const VecCtx& c, double delta, const double* out2, cudaStream_t st) {
+    k_cauchy_eval_inc<<<1, kVT, 0, st>>>(c, delta, out2);
+}
 void vk_cauchy_advance(const VecCtx& c, bool mask, int breakpoint, cudaStream_t st) {
     if (mask)
         k_cauchy_advance<true><<<1, kVT, 0, st>>>(c, breakpoint);

@@ -24,6 +24,14 @@ struct VecCtx {
 void vk_active_reset(const VecCtx& c, const double* xa, const double* sa /*nullable: use xa+sa*/, cudaStream_t st);
 void vk_cauchy_init(const VecCtx& c, bool mask, cudaStream_t st);                 // s = 0; d = P(-g) [mask]
 void vk_cauchy_eval(const VecCtx& c, double delta, cudaStream_t st);              // phi_p, phi_pp, theta, ind
+// Incremental Cauchy search (opt-in, m_lin == 0): t = J d and u = J s_c are kept as M-vectors; a breakpoint is
+//   u += theta*t ; t -= d_ind * J[:,ind]   and   phi'' = ||t||^2, phi' = u.t + g.d   (same algebra as :609-611,:633-635).
+// vk_cauchy_inc updates the local rows and writes per-CTA partials [tt, ut]; vk_cauchy_inc_reduce sums them in fixed
+// order into out2[0..2) (all-reduced by the caller); vk_cauchy_eval_inc is k_cauchy_eval with phi', phi'' from out2.
+void vk_cauchy_inc(const VecCtx& c, const double* J, long long M, double* t, double* u, double* partial2, int nblocks,
+                   int first, cudaStream_t st);
+void vk_cauchy_inc_reduce(const double* partial2, int nblocks, double* out2, cudaStream_t st);
+void vk_cauchy_eval_inc(const VecCtx& c, double delta, const double* out2, cudaStream_t st);
 void vk_cauchy_advance(const VecCtx& c, bool mask, int breakpoint, cudaStream_t st);
 void vk_gminor_nrg(const VecCtx& c, bool mask, cudaStream_t st);                  // gm = hv + g; nrg_g, nrg_gm [mask]
 void vk_norm_to(const VecCtx& c, const double* v, int which, cudaStream_t st);    // which: 0 nrg_g, 1 nrg_gm, 2 pix, 3 norm_g, 4 norm_s

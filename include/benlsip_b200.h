@@ -83,6 +83,7 @@ typedef struct bnl_stats {
     int64_t gram_count;   /* Gram formations (BNL_HESSIAN_GRAM)                                        */
     double gram_ms;
     int64_t p2p_allreduces; /* all-reduces done by the fused NVLink peer-memory kernels instead of NCCL       */
+    int64_t inc_breakpoints; /* breakpoints handled by the incremental Cauchy update (no J pass)                */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */
@@ -95,6 +96,12 @@ typedef struct bnl_inner_record {
  * fused into one HBM pass.  GRAM forms G = J'J once per Jacobian on the FP64 tensor cores (DMMA) and applies H from G:
  * same mathematics, different rounding (kappa(G) = kappa(J)^2) => opt-in, validated separately.        */
 enum { BNL_HESSIAN_MATRIX_FREE = 0, BNL_HESSIAN_GRAM = 1 };
+
+/* How cauchy_step (src/basic_tralcnlss.jl:574-639) obtains phi' and phi'' after a breakpoint.  LITERAL (default): a fresh
+ * Hd = H*d per breakpoint (:633), one pass over J each.  INCREMENTAL (opt-in, bound-only problems): d only loses one
+ * component per breakpoint, so t = J d and u = J s_c are updated in place (one strided column of J + two M-vector
+ * streams) and phi'' = ||t||^2, phi' = u.t + g.d -- same algebra and decisions, different rounding.                     */
+enum { BNL_CAUCHY_LITERAL = 0, BNL_CAUCHY_INCREMENTAL = 1 };
 
 /* Built-in device-side models (definitions in oracle/models.py, the executable spec). */
 enum { BNL_MODEL_GLM = 1, BNL_MODEL_EXPSUM = 2 };
@@ -154,6 +161,7 @@ int bnl_jv(bnl_handle h, const double* v, double* Jv_local);     /* H.J*v       
 int bnl_jtw(bnl_handle h, const double* w_local, double* JTw);   /* H.J'*w         :105,:45 */
 int bnl_gram(bnl_handle h, double* G_colmajor /*n x n or NULL*/, double* ms); /* J'J: K12, not in the reference */
 int bnl_set_hessian_mode(bnl_handle h, int32_t mode);
+int bnl_set_cauchy_mode(bnl_handle h, int32_t mode);
 
 /* ---- MixedConstraints methods (src/polyhedral_constraints.jl) --------------------------------------- */
 int bnl_project(bnl_handle h, const double* r, double* v);                 /* projection!          :158-170 */

@@ -446,6 +446,43 @@ def test_gram_mode_solve_matches_matrix_free_and_oracle(S, M, n):
     assert rel(hv_g, hv_f) < 1e-12 and abs(q_g - q_f) <= 1e-12 * q_f
 
 
+@pytest.mark.parametrize("M,n", [(4096, 64), (20000, 256), (6000, 1024)])
+def test_incremental_cauchy_mode_matches_oracle(S, M, n):
+    """Opt-in incremental Cauchy search (t = J d, u = J s_c updated per breakpoint instead of a Hessian apply each):
+    same decisions as the literal search => same iteration / breakpoint counts and final iterate as the oracle."""
+    P = GlmProblem(M, n, seed=3)
+    tr_o, tr_g = {}, {}
+    x_o, _ = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr_o)
+    S.set_problem(P.M, P.n)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+    S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+    x_g, _ = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr_g)
+    st = tr_g["stats"]
+    assert st["inc_breakpoints"] == st["breakpoints"] == tr_o.get("breakpoints", 0)
+    assert st["j_passes"] < tr_o["counters"]["hess_mul"] + tr_o["counters"]["vthv"] + tr_o["counters"]["jtw"]
+    assert (tr_g["outer_iters"], st["inner_iters"], st["minor_iters"], st["cg_iters"]) == \
+           (tr_o["outer_iters"], tr_o["inner_iters"], tr_o.get("minor_iters", 0), tr_o.get("cg_iters", 0))
+    assert rel(x_g, x_o) < 1e-10
+    assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+    for a, b in zip(tr_g["inner"], tr_o["inner"]):
+        assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"] and abs(a["mx"] - b["mx"]) <= 1e-10 * abs(b["mx"])
+    # the Cauchy point itself against the literal search and the oracle
+    S.set_cauchy_mode(B.CAUCHY_LITERAL)
+
+
+def test_incremental_cauchy_step_equals_literal(S):
+    P, x, g, H, L0, cons = _glm_state(S, 3000, 96)
+    for delta in (1e-3, 0.05, 10.0):
+        S.set_cauchy_mode(B.CAUCHY_LITERAL)
+        s_lit, pred_lit = S.inner_step(x, g, delta)
+        w_lit = S.fixvars_words()
+        S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+        s_inc, pred_inc = S.inner_step(x, g, delta)
+        assert rel(s_inc, s_lit) < 1e-12 and abs(pred_inc - pred_lit) <= 1e-12 * abs(pred_lit)
+        assert np.array_equal(S.fixvars_words(), w_lit)
+    S.set_cauchy_mode(B.CAUCHY_LITERAL)
+
+
 def test_native_outer_loop_equals_host_outer_loop(S, tmp_path):
     P = GlmProblem(4096, 64, seed=3)
     S.set_problem(P.M, P.n)
