@@ -78,6 +78,12 @@ function set_params!(s::Solver; eta1, eta2, gamma1, gamma2, kappa2, kappa3, max_
     check(s.h, ccall((:bnl_set_params, LIB), Cint, (Ptr{Cvoid}, Ref{BnlParams}), s.h, p))
 end
 
+# opt-in modes (INTEGRATION.md 2b); defaults are the reference's semantics
+const HESSIAN_MATRIX_FREE, HESSIAN_GRAM = Int32(0), Int32(1)
+const CAUCHY_LITERAL, CAUCHY_INCREMENTAL = Int32(0), Int32(1)
+set_hessian_mode!(s::Solver, mode::Int32) = check(s.h, ccall((:bnl_set_hessian_mode, LIB), Cint, (Ptr{Cvoid}, Int32), s.h, mode))
+set_cauchy_mode!(s::Solver, mode::Int32) = check(s.h, ccall((:bnl_set_cauchy_mode, LIB), Cint, (Ptr{Cvoid}, Int32), s.h, mode))
+
 # Base.:*(H::AlHessian, v) :102-106 and vthv :92-96 on the (J, C, mu) the handle currently holds
 hess_mul(s::Solver, v::Vector{Float64}) = (out = similar(v);
     check(s.h, ccall((:bnl_hess_mul, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), s.h, v, out)); out)
