@@ -38,6 +38,36 @@ def test_ctypes_struct_layouts_match_the_header():
     assert sizes == [ctypes.sizeof(B.Params), ctypes.sizeof(B.OuterParams), ctypes.sizeof(B.Stats), ctypes.sizeof(B.InnerRecord)]
 
 
+def test_plain_c_program_links_and_calls_the_library():
+    """A C99 program (no C++, no Python) links against libbenlsip_b200.so and calls it -- what a `ccall` does."""
+    prog = r'''
+#include <stdio.h>
+#include "benlsip_b200.h"
+int main(void) {
+    bnl_handle h = 0;
+    bnl_params p;
+    bnl_default_params(&p);
+    int rc = bnl_create(0, &h);
+    printf("%d %d %d %s\n", bnl_version(), bnl_device_count(), rc, bnl_status_string(rc));
+    if (rc == BNL_OK) bnl_destroy(h);
+    return (p.max_inner_iter == 500) ? 0 : 1;
+}
+'''
+    libdir = os.path.join(ROOT, "benlsip.jl_b200")
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "c.c"), os.path.join(d, "c")
+        open(c, "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe,
+                               "-L", libdir, "-lbenlsip_b200", "-Wl,-rpath," + libdir])
+        out = subprocess.check_output([exe], text=True).split(None, 3)
+    version, ndev, rc = int(out[0]), int(out[1]), int(out[2])
+    assert version >= 100
+    if ndev == 0:
+        assert rc == -9 and "no CPU path" in out[3]  # BNL_ENODEV: the library refuses to run without a B200
+    else:
+        assert rc in (0, -9)
+
+
 class _OracleBackedSolver:
     """TEST-ONLY stand-in with the slice of the Solver interface that `tralcnllss` uses."""
 
