@@ -3,38 +3,57 @@
 bench.py -- BASELINE.json's headline: "solve wall-time & J/J' matvec HBM GB/s at m=1e7 n=1024, 1/2/4/8 B200".
 
 A step = one complete `tralcnllss` solve of the synthetic bound-constrained GLM problem (cfg3: M = 1e7 residuals,
-n = 1024 parameters, box bounds, FP64) from x0: the outer augmented-Lagrangian loop runs on the host (Python
-standing in for Julia) and every subproblem goes through the C ABI (`bnl_solve_subproblem`) with HOST buffers.
-Jacobian rows are sharded over the N ranks (strong scaling: M is fixed), the one collective is the library's NCCL
-all-reduce of n+1 doubles per Hessian apply.
+n = 1024 parameters, box bounds, FP64) from x0 to the reference's default tolerances: the outer augmented-Lagrangian loop
+runs on the host (Python standing in for Julia) and every subproblem goes through the C ABI (`bnl_solve_subproblem`) with
+HOST buffers.  Jacobian rows are sharded over the N ranks (strong scaling: M is fixed); the one collective is the
+exchange of per-group sums inside the library (NVLink peer-memory stores).  Iteration counts and iterates are bit-identical
+for N = 1, 2, 4, 8 (fixed row-chunk geometry), so solve time scales on IDENTICAL work.
 
-metric  matvec_equiv_GBps: 8*M*n bytes per J.v or J'.w product the ALGORITHM performs (a Hessian apply = 2 products,
-        exactly what the reference's two DGEMVs stream) divided by time.  Same accounting on both arms.
-        NOTE the fused kernel reads J once per Hessian apply, so `value` can exceed the HBM peak; the HBM-honest
-        number is `roofline` (algorithmic bytes of ONE pass / measured kernel time).
-value   from CUDA-event time inside the library around each subproblem solve (inputs resident in HBM)
-e2e     same work / wall-clock around the public API call, host<->device copies of x, y, fixvars included
+metric  solve_wall_s (lower is better)
+value   CUDA-event time inside the library summed over the subproblem solves of one tralcnllss call (inputs resident in HBM),
+        max over ranks
+e2e     wall-clock around the public API call, host<->device copies of x, y, fixvars included, max over ranks
+roofline  the streaming Jacobian kernel (mv_stream_kernel: J'(Jv), Jv, J'w -- ONE pass over J each): algorithmic bytes of one
+        pass / average launch duration (CUDA events on the library's stream, over every launch of the timed region)
+cpu_baseline / --impl reference
+        the reference's CPU path = the literal NumPy/OpenBLAS restatement in oracle/ (Julia is not in this image), all host
+        threads, on a bounded row sample (M/256 rows, same n, full solve); `value` is that solve extrapolated linearly in M
+        to the full size (every J pass is O(M n); the sample's own seconds, counts and per-pass time are reported beside it).
 """
-import argparse
-import json
 import os
-import statistics
-import subprocess
 import sys
-import threading
-import time
+
+# the reference arm is CPU BLAS work: give it every core even when the launcher (torchrun) exported OMP_NUM_THREADS=1.
+# This must happen before NumPy / OpenBLAS are loaded.
+if "--impl" in sys.argv and "reference" in sys.argv:
+    _nc = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _nc
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import statistics  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-CFG = {"cfg3": dict(M=10_000_000, n=1024, model="glm", seed=3, noise=1e-3, cond_exp=0.0),
-       "cfg2": dict(M=1_000_000, n=256, model="expsum", seed=1, noise=1e-3, cond_exp=0.0),
-       # BASELINE config[3]: linear equalities + nonlinear (sphere) equality + box, AL loop exercised; general projection
-       "cfg4": dict(M=4_000_000, n=2048, model="glm_mixed", m_lin=64, seed=5, noise=1e-3, cond_exp=0.0)}
-METRIC = "matvec_equiv_GBps"
-UNIT = "GB/s"
+CFG = {
+    # BASELINE config[2]: the headline.  Breakpoint-dominated: projected CG never runs (J'J ~ c I at M/n = 1e4)
+    "cfg3": dict(M=10_000_000, n=1024, model="glm", seed=3, noise=1e-3, cond_exp=0.0),
+    # same family with column scaling 10^(-j/n) and a truth vector strictly inside the box: the minor iterates (projected CG,
+    # src/basic_tralcnlss.jl:690-764) carry the solve
+    "cfg3cg": dict(M=10_000_000, n=1024, model="glm", seed=3, noise=1e-3, cond_exp=1.0, interior_truth=True),
+    "cfg2": dict(M=1_000_000, n=256, model="expsum", seed=1, noise=1e-3, cond_exp=0.0),
+    # BASELINE config[3]: linear equalities + nonlinear (sphere) equality + box, AL loop exercised; general projection
+    "cfg4": dict(M=4_000_000, n=2048, model="glm_mixed", m_lin=64, seed=5, noise=1e-3, cond_exp=0.0),
+}
+METRIC = "solve_wall_s"
+UNIT = "s"
 
 
 def peaks():
@@ -45,6 +64,13 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def interior_truth(n, seed):
+    """x_true strictly inside [-1, 1]^n (no component on a bound) for the CG workload; same hash as the models."""
+    from benlsip_b200.problems import _sym
+
+    return 0.5 * _sym(seed + 2, np.zeros(1), np.arange(n))[0]
 
 
 class ClockSampler(threading.Thread):
@@ -80,77 +106,95 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def run_reference(args, cfg):
-    """The reference's CPU implementation of the path (the literal NumPy/OpenBLAS restatement in oracle/, since Julia is
-    not in this image -- DESIGN.md) on a bounded row sample of the same workload, all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import benlsip_oracle as O
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def oracle_problem(cfg, M_s):
     from oracle.models import ExpSumProblem, GlmProblem
 
-    M_s = max(cfg["M"] // args.cpu_sample_div, 1024)
     n = cfg["n"]
-    P = GlmProblem(M_s, n, seed=cfg["seed"]) if cfg["model"] == "glm" else ExpSumProblem(M_s, n, seed=cfg["seed"])
+    if cfg["model"] == "glm":
+        P = GlmProblem(M_s, n, seed=cfg["seed"], noise=cfg["noise"], cond_exp=cfg["cond_exp"])
+        if cfg.get("interior_truth"):
+            P.x_true = interior_truth(n, cfg["seed"])
+            P.y = P._gen_y()
+        return P
+    return ExpSumProblem(M_s, n, seed=cfg["seed"])
+
+
+def oracle_solve(cfg, M_s):
+    """One full solve of the row sample by the CPU restatement, with every host thread.  Returns (seconds, trace, threads)."""
+    from oracle import benlsip_oracle as O
+
+    P = oracle_problem(cfg, M_s)
+    P.design()  # problem generation is outside the timed region on both arms
+    nthreads = host_threads()
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
-    except Exception:
-        cores = os.cpu_count()
+        from threadpoolctl import threadpool_info, threadpool_limits
+        ctx = threadpool_limits(limits=nthreads)
+    except Exception:  # pragma: no cover
+        threadpool_info = None
+        ctx = None
+    tr = {}
+    t0 = time.perf_counter()
+    O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr)
+    dt = time.perf_counter() - t0
+    used = nthreads
+    if threadpool_info is not None:
+        used = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+    if ctx is not None:
+        ctx.restore_original_limits()
+    return dt, tr, used
 
-    def step():
-        tr = {}
-        t0 = time.perf_counter()
-        O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr)
-        dt = time.perf_counter() - t0
-        c = tr["counters"]
-        return dt, 8.0 * M_s * n * (c.get("jv", 0) + c.get("jtw", 0)), tr
 
+def cpu_line(cfg, M_s, dt, tr, cores):
+    c = tr["counters"]
+    passes = c.get("jv", 0) + c.get("jtw", 0)
+    scale = cfg["M"] / M_s
+    return {"value": dt * scale, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"rows 0..{M_s} of M={cfg['M']} (M/{int(round(scale))}), n={cfg['n']}, one full tralcnllss solve; "
+                      f"value = sample seconds x {scale:.0f} (every J pass is O(M n))",
+            "extrapolated_full_size_solve_s": dt * scale, "sample_solve_s": dt, "sample_rows": M_s,
+            "j_passes": passes, "s_per_pass_sample": dt / max(passes, 1), "cpu_matvec_GBps": 8.0 * M_s * cfg["n"] * passes / dt / 1e9,
+            "counts": {"outer": tr["outer_iters"], "inner": tr["inner_iters"], "minor": tr.get("minor_iters", 0),
+                       "cg": tr.get("cg_iters", 0), "breakpoints": tr.get("breakpoints", 0)}}
+
+
+def run_reference(args, cfg):
+    """--impl reference: rank 0 only; the other ranks exit without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    M_s = max(cfg["M"] // args.cpu_sample_div, 1024)
     for _ in range(args.warmup):
-        step()
-    tot_t = tot_b = 0.0
-    tr = None
+        oracle_solve(cfg, M_s)
+    tot = 0.0
+    last = None
     for _ in range(args.steps):
-        dt, b, tr = step()
-        tot_t += dt
-        tot_b += b
-    val = tot_b / tot_t / 1e9
-    sample = f"rows 0..{M_s} of M={cfg['M']} (M/{args.cpu_sample_div}), n={n}, full tralcnllss solve per step"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.config, "M": cfg["M"], "n": n, "sample_rows": M_s, "residual_family": cfg["model"],
-                       "bytes_accounting": "8*M*n per J.v or J'.w product"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "counts": {"outer": tr["outer_iters"], "inner": tr["inner_iters"], "cg": tr.get("cg_iters", 0)}}
+        dt, tr, cores = oracle_solve(cfg, M_s)
+        tot += dt
+        last = (dt, tr, cores)
+    dt = tot / args.steps
+    cb = cpu_line(cfg, M_s, dt, last[1], last[2])
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.config, "M": cfg["M"], "n": cfg["n"], "sample_rows": M_s, "residual_family": cfg["model"],
+                       "step": "one full tralcnllss solve of the row sample; value extrapolated linearly in M to the full size"},
+            "cpu_baseline": cb, "counts": cb["counts"],
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------
-def run_ours(args, cfg):
-    import torch
-    import torch.distributed as dist
-
-    import benlsip_b200 as B
+def make_solver(B, cfg, args, local_rank, world, rank, M):
     from benlsip_b200.distributed import init_solver_comm, shard_rows
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the library has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    M, n = cfg["M"], cfg["n"]
-    if args.M:
-        M = args.M
+    n = cfg["n"]
     row0, M_loc = shard_rows(M, world, rank)
     S = B.Solver(local_rank)
     info = S.device_info()
-    need = 8.0 * M_loc * n * 1.02 + 3 * 8.0 * M_loc + (1 << 30)
+    need = 8.0 * M_loc * n * 1.02 + 5 * 8.0 * M_loc + (1 << 30)
     if need > info["free_bytes"]:
         raise SystemExit(f"J shard ({need/1e9:.1f} GB) does not fit the GPU ({info['free_bytes']/1e9:.1f} GB free)")
     solve_kw = {}
@@ -166,11 +210,35 @@ def run_ours(args, cfg):
     else:
         S.set_problem(M_loc, n, M_total=M, row0=row0)
         S.use_builtin_model(B.MODEL_GLM if cfg["model"] == "glm" else B.MODEL_EXPSUM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
+        if cfg.get("interior_truth"):
+            S.model_set_truth(interior_truth(n, cfg["seed"]))
     if world > 1:
         init_solver_comm(S)
+    return S, n, M_loc, solve_kw
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    import benlsip_b200 as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the library has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    M = args.M or cfg["M"]
+    S, n, M_loc, solve_kw = make_solver(B, cfg, args, local_rank, world, rank, M)
     x0 = S.model_vectors()["x0"]
     if args.hessian == "gram":
         S.set_hessian_mode(B.HESSIAN_GRAM)
+    if args.cauchy == "literal":
+        S.set_cauchy_mode(B.CAUCHY_LITERAL)
 
     def barrier():
         if world > 1:
@@ -185,6 +253,21 @@ def run_ours(args, cfg):
         wall = time.perf_counter() - t0
         return x, tr, wall
 
+    def maxranks(*vals):
+        if world == 1:
+            return vals
+        tt = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in tt)
+
+    def extra_solve():  # one solve in the current mode, timed end to end (max over ranks)
+        barrier()
+        t0 = time.perf_counter()
+        xe, tre, _ = step()
+        barrier()
+        (te,) = maxranks(time.perf_counter() - t0)
+        return xe, tre, te
+
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
@@ -193,18 +276,16 @@ def run_ours(args, cfg):
     barrier()
     t_begin = time.perf_counter()
     dev_ms = 0.0
-    prod_bytes = 0.0
-    hm_ms = hm_cnt = launches = jpass = 0
+    mv_ms = mv_cnt = launches = jpass = 0
     h2d = d2h = 0
     tr = x = None
     for _ in range(args.steps):
         x, tr, wall = step()
         st = tr["stats"]
         dev_ms += st["solve_ms"]
-        prod_bytes += 8.0 * M * n * (st["jv"] + st["jtw"])
         jpass += st["j_passes"]
-        hm_ms += st["hess_mul_ms"]
-        hm_cnt += st["hess_mul"]
+        mv_ms += st["hess_mul_ms"] + st["vthv_ms"] + st["jtw_ms"]
+        mv_cnt += st["j_passes"] - st["gram_count"]
         launches += st["kernel_launches"]
         outer = tr["outer_iters"]
         h2d += outer * (8 * n) + 8 * ((n + 63) // 64)  # x0 per subproblem + fixvars reset
@@ -212,122 +293,127 @@ def run_ours(args, cfg):
     barrier()
     t_wall = time.perf_counter() - t_begin
     sampler.stop_flag = True
-    # extra: one solve in the opt-in Gram-apply mode (G = J'J on the FP64 tensor cores once per Jacobian), reported beside
-    # the headline, never mixed into it
-    gram_extra = None
-    if args.hessian == "matrix_free" and not args.no_gram_extra and cfg["model"] != "glm_mixed":
+    t_wall, dev_ms = maxranks(t_wall, dev_ms)
+    st = tr["stats"]
+    counts = {"outer": tr["outer_iters"], "inner": st["inner_iters"], "minor": st["minor_iters"], "cg": st["cg_iters"],
+              "breakpoints": st["breakpoints"], "hess_mul": st["hess_mul"], "vthv": st["vthv"], "jtw": st["jtw"],
+              "jac_eval": st["jac_eval"], "res_eval": st["res_eval"], "j_passes": st["j_passes"],
+              "cauchy_loop_launches": st["cauchy_loop_launches"], "cauchy_literal_evals": st["cauchy_literal_evals"],
+              "chol_rebuilds": st["chol_rebuilds"], "allreduces": st["allreduces"], "p2p_allreduces": st["p2p_allreduces"],
+              "mu": tr["mu"]}
+    phases = {"streaming_kernels_ms": st["hess_mul_ms"] + st["vthv_ms"] + st["jtw_ms"], "jacobian_generation_ms": st["jac_eval_ms"],
+              "residual_eval_ms": st["res_eval_ms"], "solve_ms": st["solve_ms"]}
+    phases["other_ms"] = phases["solve_ms"] - phases["streaming_kernels_ms"] - phases["jacobian_generation_ms"] - phases["residual_eval_ms"]
+
+    # ---- extras, reported beside (never inside) the headline ----
+    extras = {}
+    if not args.no_extras and cfg["model"] != "glm_mixed" and args.hessian == "matrix_free" and args.cauchy == "incremental":
+        # the literal Cauchy search (a Hessian apply per breakpoint, src/basic_tralcnlss.jl:633): must give the same iterate
+        S.set_cauchy_mode(B.CAUCHY_LITERAL)
+        xl, trl, tl = extra_solve()
+        stl = trl["stats"]
+        extras["literal_cauchy_mode"] = {
+            "solve_wall_s": tl, "outer": trl["outer_iters"], "inner": stl["inner_iters"], "breakpoints": stl["breakpoints"],
+            "cg": stl["cg_iters"], "hess_mul": stl["hess_mul"], "j_passes": stl["j_passes"],
+            "x_bitwise_equal_to_default": bool(np.array_equal(xl, x)),
+            "hess_mul_avg_ms": stl["hess_mul_ms"] / max(stl["hess_mul"], 1)}
+        S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+        # opt-in Gram-apply mode (G = J'J on the FP64 tensor cores once per Jacobian)
         S.set_hessian_mode(B.HESSIAN_GRAM)
-        step()  # warm-up (allocations)
-        barrier()
-        tg0 = time.perf_counter()
-        xg, trg, _ = step()
-        barrier()
-        tg = time.perf_counter() - tg0
+        xg, trg, tg = extra_solve()
         stg = trg["stats"]
         ldp = (n + 15) // 16 * 16
         ntile = (ldp + 127) // 128
         gflops = 2.0 * M_loc * (ntile * (ntile + 1) / 2) * 128 * 128
-        gram_extra = {"solve_wall_s": tg, "outer": trg["outer_iters"], "inner": stg["inner_iters"], "hess_mul": stg["hess_mul"],
-                      "j_passes": stg["j_passes"], "gram_count": stg["gram_count"],
-                      "gram_ms_avg": stg["gram_ms"] / max(stg["gram_count"], 1),
-                      "gram_tflops_per_gpu": gflops / (stg["gram_ms"] / max(stg["gram_count"], 1) * 1e-3) / 1e12 if stg["gram_ms"] > 0 else None,
-                      "x_rel_diff_vs_matrix_free": float(np.linalg.norm(xg - x) / np.linalg.norm(x)),
-                      "matvec_equiv_GBps": 8.0 * M * n * (stg["jv"] + stg["jtw"]) / tg / 1e9}
+        gavg = stg["gram_ms"] / max(stg["gram_count"], 1)
+        extras["gram_mode"] = {"solve_wall_s": tg, "outer": trg["outer_iters"], "inner": stg["inner_iters"], "hess_mul": stg["hess_mul"],
+                               "j_passes": stg["j_passes"], "gram_count": stg["gram_count"], "gram_ms_avg": gavg,
+                               "gram_tflops_per_gpu": gflops / (gavg * 1e-3) / 1e12 if gavg > 0 else None,
+                               "x_rel_diff_vs_default": float(np.linalg.norm(xg - x) / np.linalg.norm(x))}
         S.set_hessian_mode(B.HESSIAN_MATRIX_FREE)
-    # extra: one solve with the opt-in incremental Cauchy search (no Hessian apply per breakpoint)
-    inc_extra = None
-    if args.hessian == "matrix_free" and not args.no_gram_extra and cfg["model"] != "glm_mixed":
-        S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
-        step()
-        barrier()
-        ti0 = time.perf_counter()
-        xi, tri, _ = step()
-        barrier()
-        ti = time.perf_counter() - ti0
-        sti = tri["stats"]
-        inc_extra = {"solve_wall_s": ti, "outer": tri["outer_iters"], "inner": sti["inner_iters"], "breakpoints": sti["breakpoints"],
-                     "hess_mul": sti["hess_mul"], "j_passes": sti["j_passes"],
-                     "x_rel_diff_vs_default": float(np.linalg.norm(xi - x) / np.linalg.norm(x)),
-                     "matvec_equiv_GBps_literal_accounting": 8.0 * M * n * (st["jv"] + st["jtw"]) / ti / 1e9}
-        S.set_cauchy_mode(B.CAUCHY_LITERAL)
-    # max over ranks of both clocks
-    if world > 1:
-        tt = torch.tensor([t_wall, dev_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_wall, dev_ms = float(tt[0]), float(tt[1])
     if rank == 0:
         peak, peak_src = peaks()
         ld = (n + 15) // 16 * 16
         alg_bytes = 8.0 * M_loc * ld + 16.0 * n  # ONE pass over the local J shard
-        avg_ms = hm_ms / max(hm_cnt, 1)
+        avg_ms = mv_ms / max(mv_cnt, 1)
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-        value = prod_bytes / (dev_ms * 1e-3) / 1e9
-        e2e = prod_bytes / t_wall / 1e9
+        value = dev_ms * 1e-3 / args.steps
+        e2e = t_wall / args.steps
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.config, "M": M, "n": n, "residual_family": cfg["model"], "rows_per_gpu": M_loc,
-                           "parallelism": f"row-sharded x{world}", "collective": ("fused NVLink peer-memory all-reduce" if S.comm_info()["p2p_allreduce"] else ("nccl" if world > 1 else "none")), "l2": f"no flush needed: the J shard streamed by every apply is {8.0 * M_loc * n / 1e9:.1f} GB >> 126 MB L2",
-                           "bytes_accounting": "8*M*n per J.v or J'.w product; a fused Hessian apply = 2 products, 1 HBM pass",
-                           "step": "one full tralcnllss solve to the reference tolerances (defaults)"},
-                "solve_wall_s": t_wall / args.steps, "solve_device_s": dev_ms * 1e-3 / args.steps,
-                # HBM-honest whole-solve figure: bytes of J actually streamed (one pass per fused apply) / device time
-                "hbm_stream_GBps": 8.0 * M * ((n + 15) // 16 * 16) * jpass / (dev_ms * 1e-3) / 1e9,
-                "counts": {"outer": tr["outer_iters"], "inner": tr["stats"]["inner_iters"], "minor": tr["stats"]["minor_iters"],
-                           "cg": tr["stats"]["cg_iters"], "breakpoints": tr["stats"]["breakpoints"], "hess_mul": tr["stats"]["hess_mul"],
-                           "vthv": tr["stats"]["vthv"], "jtw": tr["stats"]["jtw"], "jac_eval": tr["stats"]["jac_eval"],
-                           "chol_rebuilds": tr["stats"]["chol_rebuilds"], "mu": tr["mu"],
-                           "res_eval": tr["stats"]["res_eval"], "j_passes": tr["stats"]["j_passes"], "allreduces": tr["stats"]["allreduces"],
-                           "p2p_allreduces": tr["stats"]["p2p_allreduces"]},
-                "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"]))},
-                "roofline": {"bound": "hbm", "kernel": "mv_stream_kernel<JTJV> (fused J'(Jv), one pass)", "achieved": achieved,
-                             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                             "avg_launch_ms": avg_ms, "launches_timed": hm_cnt, "algorithmic_bytes_per_launch": alg_bytes,
+                           "parallelism": f"row-sharded x{world}",
+                           "collective": ("NVLink peer-memory exchange of per-group sums" if S.comm_info()["p2p_allreduce"] else ("ncclAllGather of per-group sums" if world > 1 else "none")),
+                           "l2": f"no flush needed: the J shard streamed by every pass is {8.0 * M_loc * n / 1e9:.1f} GB >> 126 MB L2",
+                           "step": "one full tralcnllss solve to the reference tolerances (defaults), outer loop on the host, subproblems through the C ABI",
+                           "hessian": args.hessian, "cauchy": args.cauchy},
+                "counts": counts, "phases_ms_last_step": phases,
+                "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"])),
+                          "x_crc": int(np.frombuffer(x.tobytes(), dtype=np.uint64).sum() & np.uint64(0xFFFFFFFFFFFF))},
+                # J / J' matvec HBM GB/s (BASELINE metric, second half): bytes of J actually streamed / time
+                "matvec_hbm_GBps": achieved,
+                "hbm_stream_GBps_whole_solve": 8.0 * M_loc * ld * jpass / (dev_ms * 1e-3) / 1e9,
+                "roofline": {"bound": "hbm", "kernel": "mv_stream_kernel (J'(Jv) fused / Jv / J'w: one pass over J per launch)",
+                             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                             "avg_launch_ms": avg_ms, "launches_timed": mv_cnt, "algorithmic_bytes_per_launch": alg_bytes,
                              "traffic": None},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
-        line["config"]["hessian"] = args.hessian
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if world == 1 and M == CFG["cfg3"]["M"] and n == 1024 and args.hessian == "matrix_free" and os.path.exists(tp):
+        if st["cg_iters"] > 0:  # projected CG: time per iteration split into streaming and exposed latency
+            hm = st["hess_mul_ms"] / max(st["hess_mul"], 1)
+            line["cg"] = {"iters": st["cg_iters"], "hess_mul_kernel_us": 1e3 * hm,
+                          "note": "one fused J'(Jv) pass + one fused O(n) CG kernel + one host decision per iteration"}
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if world == 1 and M == CFG["cfg3"]["M"] and n == 1024 and os.path.exists(tp):
             tj = json.load(open(tp))  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
             line["roofline"]["traffic"] = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
             line["roofline"]["traffic_source"] = tj["source"]
-        if gram_extra is not None:
-            line["gram_mode"] = gram_extra
-        if inc_extra is not None:
-            line["incremental_cauchy_mode"] = inc_extra
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, cfg)
+        line.update(extras)
+        if world == 1 and not args.no_cpu_baseline and cfg["model"] != "glm_mixed":
+            cb = cpu_baseline(args, cfg, B, local_rank)
+            if "literal_cauchy_mode" in extras:
+                # the reference's own work at FULL size: J passes of the literal algorithm (counted on the GPU run of the same
+                # algorithm) x the CPU's measured seconds per pass x the row ratio
+                ref_passes = trl["stats"]["jv"] + trl["stats"]["jtw"]
+                cb["reference_j_passes_full_size"] = ref_passes
+                cb["extrapolated_full_size_solve_s_same_work"] = ref_passes * cb["s_per_pass_sample"] * (cfg["M"] / cb["sample_rows"])
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     S.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, cfg):
-    """Oracle ('port') timed on this host's cores on a bounded row sample of the same workload (~10-30 s)."""
-    if cfg["model"] == "glm_mixed":
-        return None
-    from oracle import benlsip_oracle as O
-    from oracle.models import ExpSumProblem, GlmProblem
-
+def cpu_baseline(args, cfg, B, local_rank):
+    """Oracle ('port') timed on this host's cores on a bounded row sample of the same workload (~10-30 s), extrapolated to the
+    full size -- plus the SAME sample problem solved on the GPU: identical inputs, counts compared."""
     M_s = max(cfg["M"] // args.cpu_sample_div, 1024)
-    n = cfg["n"]
-    P = GlmProblem(M_s, n, seed=cfg["seed"]) if cfg["model"] == "glm" else ExpSumProblem(M_s, n, seed=cfg["seed"])
+    dt, tr, cores = oracle_solve(cfg, M_s)
+    cb = cpu_line(cfg, M_s, dt, tr, cores)
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
-    except Exception:
-        cores = os.cpu_count()
-    tr = {}
-    t0 = time.perf_counter()
-    O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr)
-    dt = time.perf_counter() - t0
-    c = tr["counters"]
-    val = 8.0 * M_s * n * (c.get("jv", 0) + c.get("jtw", 0)) / dt / 1e9
-    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
-            "sample": f"rows 0..{M_s} of M={cfg['M']} (M/{args.cpu_sample_div}), n={n}, one full tralcnllss solve",
-            "counts": {"outer": tr["outer_iters"], "inner": tr["inner_iters"], "cg": tr.get("cg_iters", 0)}}
+        T = B.Solver(local_rank)
+        T.set_problem(M_s, cfg["n"])
+        T.use_builtin_model(B.MODEL_GLM if cfg["model"] == "glm" else B.MODEL_EXPSUM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
+        if cfg.get("interior_truth"):
+            T.model_set_truth(interior_truth(cfg["n"], cfg["seed"]))
+        x0 = T.model_vectors()["x0"]
+        B.tralcnllss(x0, None, None, None, None, None, None, None, None, solver=T)  # warm-up
+        T.reset_stats()
+        trg = {}
+        t0 = time.perf_counter()
+        xg, _ = B.tralcnllss(x0, None, None, None, None, None, None, None, None, solver=T, trace=trg)
+        tg = time.perf_counter() - t0
+        sg = trg["stats"]
+        gc = {"outer": trg["outer_iters"], "inner": sg["inner_iters"], "minor": sg["minor_iters"], "cg": sg["cg_iters"],
+              "breakpoints": sg["breakpoints"]}
+        cb["same_problem"] = {"rows": M_s, "gpu_solve_wall_s": tg, "cpu_solve_wall_s": dt, "gpu_counts": gc,
+                              "counts_equal": gc == cb["counts"],
+                              "x_rel_diff": float(np.linalg.norm(xg - tr["x"]) / np.linalg.norm(tr["x"]))}
+        T.close()
+    except Exception as e:  # pragma: no cover
+        cb["same_problem"] = {"error": str(e)}
+    return cb
 
 
 def main():
@@ -346,9 +432,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hessian", default="matrix_free", choices=["matrix_free", "gram"],
                     help="matrix_free = the reference's J'(Jv) semantics (default, parity mode); gram = opt-in DMMA Gram-apply mode")
-    ap.add_argument("--no-gram-extra", action="store_true", help="skip the extra (untimed-in-headline) Gram-mode solve")
+    ap.add_argument("--cauchy", default="incremental", choices=["incremental", "literal"],
+                    help="incremental = device-side guarded breakpoint loop (default; bit-identical iterates); literal = a Hessian apply per breakpoint")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra literal-Cauchy and Gram-mode solves reported beside the headline")
     args = ap.parse_args()
-    cfg = CFG[args.config]
+    cfg = dict(CFG[args.config])
+    if args.M:
+        cfg["M"] = args.M
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

@@ -70,7 +70,8 @@ class Stats(C.Structure):
                                           "vthv", "jtw", "jv", "res_eval", "jac_eval", "chol_rebuilds", "allreduces")] + \
                [(k, C.c_double) for k in ("hess_mul_ms", "vthv_ms", "jtw_ms", "res_eval_ms", "jac_eval_ms", "solve_ms")] + \
                [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double),
-                ("p2p_allreduces", C.c_int64), ("inc_breakpoints", C.c_int64)]
+                ("p2p_allreduces", C.c_int64), ("inc_breakpoints", C.c_int64), ("cauchy_loop_launches", C.c_int64),
+                ("cauchy_literal_evals", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -110,6 +111,7 @@ def load_library(build_if_missing: bool = False):
         "bnl_set_params": ([H, C.POINTER(Params)], C.c_int),
         "bnl_comm_unique_id": ([C.c_void_p], C.c_int), "bnl_comm_init": ([H, C.c_int, C.c_int, C.c_void_p], C.c_int),
         "bnl_comm_info": ([H, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
+        "bnl_shard_rows": ([i64, i32, i32, C.POINTER(i64), C.POINTER(i64)], C.c_int),
         "bnl_set_problem": ([H, i64, i64, i64, i32, i32, i32, _DP, _DP, _DP], C.c_int),
         "bnl_use_builtin_model": ([H, i32, _DP, i32, C.c_uint32], C.c_int),
         "bnl_use_callbacks": ([H, CALLBACK, CALLBACK, CALLBACK, CALLBACK, C.c_void_p], C.c_int),
@@ -130,6 +132,8 @@ def load_library(build_if_missing: bool = False):
         "bnl_get_chol": ([H, _DP, C.POINTER(i32)], C.c_int),
         "bnl_cauchy_step": ([H, _DP, _DP, dbl, _DP], C.c_int),
         "bnl_projected_cg": ([H, _DP, _DP, _DP, dbl, _DP, C.POINTER(i32), C.POINTER(i32)], C.c_int),
+        "bnl_projected_cg_bounds": ([H, _DP, _DP, _DP, _DP, C.POINTER(i32), C.POINTER(i32)], C.c_int),
+        "bnl_linesearch": ([H, _DP, _DP, _DP, _DP, _DP], C.c_int),
         "bnl_inner_step": ([H, _DP, _DP, dbl, _DP, _DP], C.c_int),
         "bnl_new_point": ([H, _DP, _DP, dbl, _DP, _DP, _DP], C.c_int),
         "bnl_solve_subproblem": ([H, _DP, _DP, dbl, dbl, _DP, _DP, _DP], C.c_int),
@@ -146,6 +150,17 @@ def load_library(build_if_missing: bool = False):
     lib._bnl_signatures = sig
     _lib = lib
     return lib
+
+
+def shard_rows(M_total: int, nranks: int, rank: int):
+    """(row0, M_local) of rank `rank` of `nranks` in {1, 2, 4, 8} (`bnl_shard_rows`): whole groups of the fixed row geometry,
+    so every row reduction is bit-identical for any supported GPU count.  Pure host function."""
+    lib = load_library()
+    r0, ml = C.c_int64(), C.c_int64()
+    rc = lib.bnl_shard_rows(int(M_total), int(nranks), int(rank), C.byref(r0), C.byref(ml))
+    if rc != 0:
+        raise ValueError(f"bnl_shard_rows(M_total={M_total}, nranks={nranks}, rank={rank}): nranks must be 1, 2, 4 or 8")
+    return int(r0.value), int(ml.value)
 
 
 def declared_symbols():
@@ -350,7 +365,8 @@ class Solver:
         return G, ms.value
 
     def set_cauchy_mode(self, mode):
-        """CAUCHY_LITERAL (reference: a Hessian apply per breakpoint, default) or CAUCHY_INCREMENTAL (bound-only problems)."""
+        """CAUCHY_INCREMENTAL (default: device-side guarded breakpoint loop, bit-identical Cauchy point) or CAUCHY_LITERAL
+        (the reference's Hessian apply per breakpoint)."""
         self._ck(self.lib.bnl_set_cauchy_mode(self.h, int(mode)))
 
     def set_hessian_mode(self, mode):
@@ -436,6 +452,21 @@ class Solver:
         self._ck(self.lib.bnl_projected_cg(self.h, _p(_vec(x, self.n)), _p(_vec(s, self.n)), _p(_vec(g_minor, self.n)),
                                            float(delta), _p(w), C.byref(st), C.byref(it)))
         return w, (None if st.value == CG_NOTHING else st.value), it.value
+
+    def projected_cg_bounds(self, g_minor, w_l, w_u):
+        """`projected_cg(g_minor, H, w_l, w_u, lincons, kappa2)` (:690-764) with explicit step bounds and the current fixvars."""
+        w = np.empty(self.n)
+        st, it = C.c_int32(), C.c_int32()
+        self._ck(self.lib.bnl_projected_cg_bounds(self.h, _p(_vec(g_minor, self.n)), _p(_vec(w_l, self.n)), _p(_vec(w_u, self.n)),
+                                                  _p(w), C.byref(st), C.byref(it)))
+        return w, (None if st.value == CG_NOTHING else st.value), it.value
+
+    def linesearch(self, g_model, w, w_l, w_u):
+        """`linesearch(g_model, H, w, w_l, w_u, lincons.fixvars)` (:766-791) -> alpha."""
+        out = C.c_double()
+        self._ck(self.lib.bnl_linesearch(self.h, _p(_vec(g_model, self.n)), _p(_vec(w, self.n)), _p(_vec(w_l, self.n)),
+                                         _p(_vec(w_u, self.n)), C.byref(out)))
+        return out.value
 
     def inner_step(self, x, g, delta):
         """`inner_step(...)` (:394-460) -> (s, model_reduction); mutates the active set."""

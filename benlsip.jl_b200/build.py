@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbenlsip_b200.so")
-SOURCES = ["matvec.cu", "vecops.cu", "models.cu", "dense.cu", "gram.cu", "p2p.cu", "solver.cu", "capi.cu"]
+SOURCES = ["matvec.cu", "vecops.cu", "models.cu", "dense.cu", "gram.cu", "p2p.cu", "cauchy_loop.cu", "solver.cu", "capi.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -84,6 +84,19 @@ int bnl_create(int device, bnl_handle* out) {
     }
     cudaMemset(h->sd, 0, sizeof(Scal));
     memset(h->sh, 0, sizeof(Scal));
+    // group mailbox of the row reductions (p2p.h): local until bnl_comm_init maps it into the peers
+    if (cudaMalloc(&h->p2p_buf, p2p_buffer_bytes()) != cudaSuccess || cudaMemset(h->p2p_buf, 0, p2p_buffer_bytes()) != cudaSuccess ||
+        cudaMalloc(&h->p2p_counter, 256) != cudaSuccess || cudaMemset(h->p2p_counter, 0, 256) != cudaSuccess) {
+        bnl_destroy(h);
+        return BNL_EOOM;
+    }
+    p2p_local_setup(h);
+    {
+        const char* env = getenv("BNL_CAUCHY");
+        h->cauchy_mode = (env && env[0] == 'l') ? BNL_CAUCHY_LITERAL : BNL_CAUCHY_INCREMENTAL;
+        const char* gd = getenv("BNL_CAUCHY_GUARD");
+        if (gd && atof(gd) > 0.0) h->cauchy_guard = atof(gd);
+    }
     cudaEventCreate(&h->ev_t0);
     cudaEventCreate(&h->ev_t1);
     *out = h;
@@ -143,41 +156,75 @@ int bnl_comm_unique_id(void* id128) {
     return BNL_OK;
 }
 
+static void comm_teardown(S* h) {
+    cudaStreamSynchronize(h->stream);
+    for (int r2 = 0; r2 < kP2PMaxRanks; ++r2) {
+        if (h->p2p_opened[r2]) cudaIpcCloseMemHandle(h->p2p_opened[r2]);
+        h->p2p_opened[r2] = nullptr;
+    }
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+    h->p2p_on = false;
+    h->nranks = 1;
+    h->rank = 0;
+    p2p_local_setup(h);
+}
+
 int bnl_comm_init(bnl_handle h, int nranks, int rank, const void* id128) {
     if (!valid(h) || nranks < 1 || rank < 0 || rank >= nranks) return BNL_EINVAL;
+    if (kGroups % nranks != 0 || nranks > kP2PMaxRanks)
+        return h->fail(BNL_EINVAL, "nranks = %d: the row geometry has %d groups, nranks must be 1, 2, 4 or 8", nranks, kGroups);
+    CK(cudaSetDevice(h->device));
+    comm_teardown(h);  // a second call replaces the previous communicator / peer mappings
+    h->comm_set = true;
     if (nranks == 1) {
-        h->nranks = 1;
-        h->rank = 0;
+        if (h->problem_set) {
+            RET(resolve_geometry(h));
+            RET(alloc_row_buffers(h));
+        }
         return BNL_OK;
     }
     if (!id128) return BNL_EINVAL;
     if (!g_nccl.load()) return h->fail(BNL_ENCCL, "cannot dlopen libnccl.so.2");
-    CK(cudaSetDevice(h->device));
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
     if (r != ncclSuccess) return h->fail(BNL_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     h->nranks = nranks;
     h->rank = rank;
-    // ---- peer-memory all-reduce over NVLink (p2p.h): exchange CUDA-IPC handles with ncclAllGather ----
+    auto min_over_ranks = [&](int v) -> int {  // also a barrier
+        int* dv = nullptr;
+        if (cudaMalloc(&dv, sizeof(int)) != cudaSuccess) return 0;
+        cudaMemcpy(dv, &v, sizeof(int), cudaMemcpyHostToDevice);
+        g_nccl.AllReduce(dv, dv, 1, ncclInt, ncclMin, h->comm, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(&v, dv, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(dv);
+        return v;
+    };
+    // ---- map every rank's mailbox into every peer (CUDA IPC; handles exchanged with ncclAllGather) ----
     const char* env = getenv("BNL_P2P_ALLREDUCE");
-    const bool want = !(env && env[0] == '0') && nranks <= kP2PMaxRanks && g_nccl.AllGather != nullptr;
-    int ok = want ? 1 : 0;
-    char* dh = nullptr;
-    std::vector<cudaIpcMemHandle_t> all(nranks);
+    // every rank must take the same branch BEFORE the all-gather below: agree on "want" first (min over ranks)
+    const int want = min_over_ranks((!(env && env[0] == '0') && g_nccl.AllGather != nullptr) ? 1 : 0);
+    int ok = want;
     if (want) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-        const size_t bytes = std::max<size_t>(p2p_buffer_bytes(nranks), (size_t)4 << 20);
+        char* dh = nullptr;
+        std::vector<cudaIpcMemHandle_t> all(nranks);
         cudaIpcMemHandle_t mine;
-        ok = ok && cudaMalloc(&h->p2p_buf, bytes) == cudaSuccess && cudaMemset(h->p2p_buf, 0, bytes) == cudaSuccess &&
-             cudaMalloc(&h->p2p_counter, 256) == cudaSuccess && cudaMemset(h->p2p_counter, 0, 256) == cudaSuccess &&
-             cudaIpcGetMemHandle(&mine, h->p2p_buf) == cudaSuccess && cudaMalloc(&dh, (size_t)nranks * 64) == cudaSuccess;
-        if (ok) {
+        int mine_ok = cudaMemset(h->p2p_buf, 0, p2p_buffer_bytes()) == cudaSuccess && cudaMemset(h->p2p_counter, 0, 256) == cudaSuccess &&
+                      cudaIpcGetMemHandle(&mine, h->p2p_buf) == cudaSuccess && cudaMalloc(&dh, (size_t)nranks * 64) == cudaSuccess;
+        if (!mine_ok) memset(&mine, 0, sizeof mine);
+        if (dh) {
             cudaMemcpy(dh + (size_t)rank * 64, &mine, 64, cudaMemcpyHostToDevice);
+            // every rank enters the collective, whatever happened locally
             ok = g_nccl.AllGather(dh + (size_t)rank * 64, dh, 64, ncclChar, h->comm, h->stream) == ncclSuccess &&
                  cudaStreamSynchronize(h->stream) == cudaSuccess &&
-                 cudaMemcpy(all.data(), dh, (size_t)nranks * 64, cudaMemcpyDeviceToHost) == cudaSuccess;
+                 cudaMemcpy(all.data(), dh, (size_t)nranks * 64, cudaMemcpyDeviceToHost) == cudaSuccess && mine_ok;
+        } else {
+            ok = 0;
         }
+        ok = min_over_ranks(ok);  // nobody opens handles unless every rank exported one
         for (int r2 = 0; ok && r2 < nranks; ++r2) {
             void* base = h->p2p_buf;
             if (r2 != rank) {
@@ -185,28 +232,34 @@ int bnl_comm_init(bnl_handle h, int nranks, int rank, const void* id128) {
                 if (ok) h->p2p_opened[r2] = base;
             }
             h->p2p.mbox[r2] = static_cast<double*>(base);
-            h->p2p.flag[r2] = p2p_flags_of(static_cast<double*>(base), nranks);
+            h->p2p.flag[r2] = p2p_flags_of(static_cast<double*>(base));
+            h->p2p.ll[r2] = p2p_ll_of(static_cast<double*>(base));
         }
         cudaGetLastError();
+        if (dh) cudaFree(dh);
     }
     // all ranks must agree (min over ranks); this all-reduce is also the barrier after everyone's memset
-    int* dok = nullptr;
-    if (cudaMalloc(&dok, sizeof(int)) == cudaSuccess) {
-        cudaMemcpy(dok, &ok, sizeof(int), cudaMemcpyHostToDevice);
-        g_nccl.AllReduce(dok, dok, 1, ncclInt, ncclMin, h->comm, h->stream);
-        cudaStreamSynchronize(h->stream);
-        cudaMemcpy(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost);
-        cudaFree(dok);
-    } else {
-        ok = 0;
-    }
-    if (dh) cudaFree(dh);
+    ok = min_over_ranks(ok);
     h->p2p.nranks = nranks;
     h->p2p.rank = rank;
-    h->p2p.done_counter = h->p2p_counter;
-    h->p2p.timeout_flag = &h->sd->p2p_timeout;
+    h->p2p.mbox[rank] = h->p2p_buf;
+    h->p2p.flag[rank] = p2p_flags_of(h->p2p_buf);
+    h->p2p.ll[rank] = p2p_ll_of(h->p2p_buf);
     h->p2p_on = ok != 0;
     h->p2p_epoch = 0;
+    h->ll_epoch = 0;
+    if (h->problem_set) {
+        RET(resolve_geometry(h));
+        RET(alloc_row_buffers(h));
+    }
+    return BNL_OK;
+}
+
+int bnl_shard_rows(int64_t M_total, int32_t nranks, int32_t rank, int64_t* row0, int64_t* M_local) {
+    RowGeom g{};
+    if (!geom_make(M_total, nranks, rank, &g)) return BNL_EINVAL;
+    if (row0) *row0 = g.row0;
+    if (M_local) *M_local = g.local_rows();
     return BNL_OK;
 }
 
@@ -236,8 +289,9 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
     h->p = p;
     h->mask = (m_lin == 0);
     size_t optin = h->prop.sharedMemPerBlockOptin;
-    h->plan = mv_make_plan(M_local, n, h->prop.multiProcessorCount, optin);
+    h->plan = mv_make_plan(n, optin);
     if (!h->plan.supported) return h->fail(BNL_EDIM, "n = %d unsupported by the streaming kernels (n <= 8192)", n);
+    RET(resolve_geometry(h));
     const size_t ld = h->ld;
     const size_t vlen = ld + kColAlign;  // +16: slot [ld] carries ||Jv||^2
     const int nvec = 17;
@@ -267,9 +321,7 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
     h->vc.cv = cpool + 2 * pc * ld;
     h->vc.pvec = h->vc.cv + pc;
     // (cpool is owned through vc.C: freed with the problem)
-    CK(cudaMalloc(&h->partial, (size_t)h->plan.grid * h->plan.pstride * sizeof(double)));
-    CK(cudaMemset(h->partial, 0, (size_t)h->plan.grid * h->plan.pstride * sizeof(double)));
-    CK(cudaMalloc(&h->sumsq_partial, h->sumsq_blocks * sizeof(double)));
+    RET(alloc_row_buffers(h));
     CK(cudaMalloc(&h->d_words, ((n + 63) / 64 + 1) * sizeof(unsigned long long)));
     CK(cudaMalloc(&h->d_idx, vlen * sizeof(long long)));
     CK(cudaMalloc(&h->d_count, sizeof(int)));
@@ -284,6 +336,8 @@ int bnl_set_problem(bnl_handle h, int64_t M_local, int64_t M_total, int64_t row0
     if (xupp) std::copy(xupp, xupp + n, up.begin());
     RET(put_vec(h, lo.data(), h->vc.xlow, n));
     RET(put_vec(h, up.data(), h->vc.xupp, n));
+    h->h_xlow = lo;
+    h->h_xupp = up;
     // linear equalities: A (column-major m_lin x n) -> row-major m_lin x ld; chol_aat = cholesky(A*A') :206
     if (m_lin > 0) {
         double* dA = nullptr;
@@ -380,6 +434,8 @@ int bnl_use_builtin_model(bnl_handle h, int32_t model_id, const double* params, 
     // the model's own box replaces whatever bnl_set_problem was given
     RET(put_vec(h, h->m_xlow.data(), h->vc.xlow, n));
     RET(put_vec(h, h->m_xupp.data(), h->vc.xupp, n));
+    h->h_xlow = h->m_xlow;
+    h->h_xupp = h->m_xupp;
     RET(sync(h));
     h->have_J = false;
     return BNL_OK;
@@ -543,7 +599,8 @@ int bnl_jv(bnl_handle h, const double* v, double* Jv_local) {
     if (!h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
     if (!h->tvec) CK(cudaMalloc(&h->tvec, std::max<size_t>(h->M, 16) * sizeof(double)));
     RET(put_vec(h, v, h->vc.t2, h->n));
-    CK(mv_launch(MODE_JV, h->plan, h->J, h->M, h->vc.t2, nullptr, h->tvec, h->partial, h->vc.hv, h->stream));
+    CK(mv_launch(MODE_JV, h->plan, h->geo, h->J, h->vc.t2, nullptr, h->tvec, h->partial, h->stream));
+    RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, h->ld, h->ld + 1, h->vc.hv));
     RET(sync(h));
     h->st.jv++;
     if (Jv_local && h->M > 0) RET(get_vec(h, h->tvec, Jv_local, h->M));
@@ -769,11 +826,45 @@ int bnl_projected_cg(bnl_handle h, const double* x, const double* s, const doubl
     RET(put_vec(h, s, h->vc.s, h->n));
     RET(put_vec(h, g_minor, h->vc.gm, h->n));
     int status = 0, it = 0;
-    RET(minor_iterate(h, delta, &status, &it, false));
+    RET(minor_iterate(h, delta, &status, &it, false, false));
     RET(sync(h));
     RET(get_vec(h, h->vc.w, w, h->n));
     if (cg_status) *cg_status = status;
     if (iters) *iters = it;
+    return BNL_OK;
+}
+
+// projected_cg(g_minor, H, w_l, w_u, lincons, kappa2) with the CALLER's step bounds (src/basic_tralcnlss.jl:690-697): reaches
+// the alpha > gamma / bound_hit branch (:735-737) that minor_iterate's own bounds (trap T1) never trigger.
+int bnl_projected_cg_bounds(bnl_handle h, const double* g_minor, const double* w_l, const double* w_u, double* w,
+                            int32_t* cg_status, int32_t* iters) {
+    ENTER();
+    if (!g_minor || !w_l || !w_u || !w) return BNL_EINVAL;
+    RET(put_vec(h, g_minor, h->vc.gm, h->n));
+    RET(put_vec(h, w_l, h->vc.wl, h->n));
+    RET(put_vec(h, w_u, h->vc.wu, h->n));
+    int status = 0, it = 0;
+    RET(minor_iterate(h, 0.0, &status, &it, false, true));
+    RET(sync(h));
+    RET(get_vec(h, h->vc.w, w, h->n));
+    if (cg_status) *cg_status = status;
+    if (iters) *iters = it;
+    return BNL_OK;
+}
+
+// linesearch(g_model, H, w, w_l, w_u, fix_bounds) (src/basic_tralcnlss.jl:766-791) with the current fixvars -> alpha
+int bnl_linesearch(bnl_handle h, const double* g_model, const double* w, const double* w_l, const double* w_u, double* alpha) {
+    ENTER();
+    if (!g_model || !w || !w_l || !w_u || !alpha) return BNL_EINVAL;
+    RET(put_vec(h, g_model, h->vc.gm, h->n));
+    RET(put_vec(h, w, h->vc.w, h->n));
+    RET(put_vec(h, w_l, h->vc.wl, h->n));
+    RET(put_vec(h, w_u, h->vc.wu, h->n));
+    CK(cudaMemsetAsync(&h->sd->cg_neg_curv, 0, sizeof(int), h->stream));
+    RET(vthv_dev(h, h->vc.w));          // :775
+    vk_minor_finish(h->vc, h->stream);  // alpha = min(alpha_opt, alpha_allowed) :776-790 (also scales w and adds it to s: unused here)
+    RET(sync(h));
+    *alpha = h->sh->alpha_ls;
     return BNL_OK;
 }
 
@@ -877,20 +968,23 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
         if (rep == 0) CK(cudaEventRecord(e0, h->stream));
         switch (kind) {
             case 0:
-                CK(mv_launch(MODE_JTJV, h->plan, h->J, h->M, h->vc.x, nullptr, nullptr, h->partial, h->vc.t1, h->stream));
+                CK(mv_launch(MODE_JTJV, h->plan, h->geo, h->J, h->vc.x, nullptr, nullptr, h->partial, h->stream));
+                RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, 0, h->ld + 1, h->vc.t1));
                 bytes = Jbytes + 16.0 * h->n;
                 break;
             case 1:
-                CK(mv_launch(MODE_JV, h->plan, h->J, h->M, h->vc.x, nullptr, nullptr, h->partial, h->vc.t1, h->stream));
+                CK(mv_launch(MODE_JV, h->plan, h->geo, h->J, h->vc.x, nullptr, nullptr, h->partial, h->stream));
+                RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, h->ld, h->ld + 1, h->vc.t1));
                 bytes = Jbytes + 8.0 * h->n;
                 break;
             case 2:
-                CK(mv_launch(MODE_JTW, h->plan, h->J, h->M, nullptr, h->r, nullptr, h->partial, h->vc.t1, h->stream));
+                CK(mv_launch(MODE_JTW, h->plan, h->geo, h->J, nullptr, h->r, nullptr, h->partial, h->stream));
+                RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, 0, h->ld, h->vc.t1));
                 bytes = Jbytes + 8.0 * h->M + 8.0 * h->n;
                 break;
             case 3:
-                CK(model_residual(margs(h), h->vc.x, h->ydata, h->r_trial, h->sumsq_partial, h->sumsq_blocks, &h->sd->sumsq_r,
-                                  h->stream));
+                CK(model_residual(margs(h), h->vc.x, h->ydata, h->r_trial, h->rpartial, h->stream));
+                RET(row_reduce(h, h->rpartial, 1, 1, 0, 1, &h->sd->sumsq_r));
                 bytes = 16.0 * h->M;
                 break;
             case 4:
@@ -914,23 +1008,86 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
     return BNL_OK;
 }
 
+// ---- benlsip.out log format (src/misc.jl:1-80): Julia's Printf prints non-finite values as NaN / Inf / -Inf ----------------
+static std::string jl_e(int prec, double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "Inf" : "-Inf";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.*e", prec, v);
+    return buf;
+}
+static void log_header(FILE* io, S* h, const bnl_outer_params& op) {  // print_tralcnllss_header, src/misc.jl:1-45
+    const std::string stars(64, '*'), blank = "*" + std::string(62, ' ') + "*";
+    int nlow = 0, nupp = 0;
+    for (int i = 0; i < h->n; ++i) {
+        nlow += std::isfinite(h->h_xlow[i]) ? 1 : 0;
+        nupp += std::isfinite(h->h_xupp[i]) ? 1 : 0;
+    }
+    fprintf(io, "\n\n%s\n%s\n", stars.c_str(), blank.c_str());
+    fprintf(io, "*%sBEnlsip.jl v-DEV%s*\n%s\n", std::string(23, ' ').c_str(), std::string(23, ' ').c_str(), blank.c_str());
+    fprintf(io, "*                   Better version of ENLSIP                   *\n%s\n%s\n", blank.c_str(), stars.c_str());
+    fprintf(io, "\nProblem dimensions\n");
+    fprintf(io, "Number of parameters.................: %5i\n", h->n);
+    fprintf(io, "Number of residuals..................: %5lli\n", (long long)h->M_total);
+    fprintf(io, "Number of nonlinear constraints......: %5i\n", h->p);
+    fprintf(io, "Number of linear constraints.........: %5i\n", h->m_lin);
+    fprintf(io, "Number of lower bounds...............: %5i\n", nlow);
+    fprintf(io, "Number of upper bounds...............: %5i\n", nupp);
+    fprintf(io, "\nAlgorithm parameters\n");
+    // the reference passes (feas_tol, crit_tol) into the (crit_tol, feas_tol) slots (src/basic_tralcnlss.jl:213-226): kept
+    fprintf(io, "Optimality tolerance.................................: %.6e\n", op.feas_tol);
+    fprintf(io, "Nonlinear constraints feasibility tolerance..........: %.6e\n", op.crit_tol);
+    fprintf(io, "Increase penalty parameter factor....................: %5f\n", op.tau);
+    fprintf(io, "Step acceptance treshold.............................: %5f\n", h->prm.eta1);
+    fprintf(io, "Great step acceptance treshold.......................: %5f\n", h->prm.eta2);
+    fprintf(io, "Trust region increase factor.........................: %5f\n", h->prm.gamma2);
+    fprintf(io, "Trust region decrease factor.........................: %5f\n", h->prm.gamma1);
+    fprintf(io, "\n\n\n");
+}
+static void log_outer(FILE* io, int k, double objective, double nl_feas, double mu, double pix, double omega, bool first) {
+    // print_outer_iter_header, src/misc.jl:47-68
+    const std::string bar(80, '=');
+    fprintf(io, "\n%s\n                          Outer iter %d\n  objective    nl feasibility     \xce\xbc      criticality   tolerance\n",
+            bar.c_str(), k);
+    if (first)
+        fprintf(io, "%s   %s  %s        -         %s", jl_e(7, objective).c_str(), jl_e(6, nl_feas).c_str(), jl_e(2, mu).c_str(),
+                jl_e(2, omega).c_str());
+    else
+        fprintf(io, "%s   %s  %s     %s     %s", jl_e(7, objective).c_str(), jl_e(6, nl_feas).c_str(), jl_e(2, mu).c_str(),
+                jl_e(2, pix).c_str(), jl_e(2, omega).c_str());
+    fprintf(io, "\n%s\niter     AL value       ||s||        \xce\x94          \xcf\x81\n", bar.c_str());
+}
+
 // ---- tralcnllss :167-298 (outer loop inside the library) ---------------------------------
+// Every rank of a sharded run must make the same call; log_path may differ per rank (typically non-NULL on rank 0 only): the
+// objective of the log line (:292) is evaluated on every rank regardless, as the reference does, so the collective sequence
+// never depends on who logs.
 int bnl_tralcnllss(bnl_handle h, const double* x0, const bnl_outer_params* op_in, const char* log_path, double* x_out,
                    double* y_out, double* final_mu, double* final_pix) {
     ENTER();
+    if (!x0) return h->fail(BNL_EINVAL, "x0 is NULL");
     bnl_outer_params op;
     if (op_in)
         op = *op_in;
     else
         bnl_default_outer_params(&op);
-    FILE* log = log_path ? fopen(log_path, "w") : nullptr;
+    FILE* log = nullptr;
+    if (log_path) {
+        log = fopen(log_path, "w");
+        if (!log) return h->fail(BNL_EINVAL, "cannot open log file %s", log_path);
+    }
     const int n = h->n, p = h->p;
     std::vector<double> x(x0, x0 + n), y(p, 0.0), cx(p, 0.0), xn(n), cxn(p, 0.0);
     double mu = op.mu0;
     double omega = op.omega0 / std::pow(mu, op.k_crit), eta = op.eta0 / std::pow(mu, op.k_feas);  // :153-163
     int rc = BNL_OK;
+    // rx = residuals(x); cx = nlconstraints(x)  :209-210
+    double ss0 = 0.0;
+    rc = bnl_residuals(h, x.data(), nullptr, &ss0);
+    if (rc == BNL_OK && p > 0) rc = bnl_nlcons(h, x.data(), cx.data(), nullptr);
+    if (log && rc == BNL_OK) log_header(log, h, op);  // :213-226
     // least_squares_multipliers :887-903 : y = -(CC')^{-1} C J'r  (p small: host arithmetic on device-computed J'r and C)
-    if (p > 0) {
+    if (p > 0 && rc == BNL_OK) {
         std::vector<double> g(n);
         // g = jac_res(x)' * residuals(x)   :893
         rc = put_vec(h, x.data(), h->vc.x, n);
@@ -990,15 +1147,10 @@ int bnl_tralcnllss(bnl_handle h, const double* x0, const bnl_outer_params* op_in
     bool first_order_critical = false;
     int outer_iter = 1;
     double pix = kInf;
-    if (log && rc == BNL_OK) {
-        double ss = 0.0;
-        bnl_residuals(h, x.data(), nullptr, &ss);
+    if (log && rc == BNL_OK) {  // :237-245
         double nc = 0.0;
         for (double v : cx) nc += v * v;
-        fprintf(log, "\n%s\n                          Outer iter %d\n  objective    nl feasibility     \xce\xbc      criticality   tolerance\n",
-                std::string(80, '=').c_str(), outer_iter);
-        fprintf(log, "%.7e   %.6e  %.2e        -         %.2e", ss, std::sqrt(nc), mu, omega);
-        fprintf(log, "\n%s\niter     AL value       ||s||        \xce\x94          \xcf\x81\n", std::string(80, '=').c_str());
+        log_outer(log, outer_iter, ss0, std::sqrt(nc), mu, 0.0, omega, true);
     }
     while (rc == BNL_OK && !first_order_critical && outer_iter <= op.max_outer_iter) {  // :246
         rc = solve_subproblem_host(h, x.data(), y.data(), mu, omega, xn.data(), cxn.data(), &pix, log);
@@ -1022,14 +1174,10 @@ int bnl_tralcnllss(bnl_handle h, const double* x0, const bnl_outer_params* op_in
         }
         ++outer_iter;
         h->st.outer_iters++;
-        if (log) {
-            double ss = 0.0;
-            bnl_residuals(h, x.data(), nullptr, &ss);  // objective :292
-            fprintf(log, "\n%s\n                          Outer iter %d\n  objective    nl feasibility     \xce\xbc      criticality   tolerance\n",
-                    std::string(80, '=').c_str(), outer_iter);
-            fprintf(log, "%.7e   %.6e  %.2e     %.2e     %.2e", ss, feas, mu, pix, omega);
-            fprintf(log, "\n%s\niter     AL value       ||s||        \xce\x94          \xcf\x81\n", std::string(80, '=').c_str());
-        }
+        double ss = 0.0;
+        rc = bnl_residuals(h, x.data(), nullptr, &ss);  // objective = dot(rx,rx) :292 -- on every rank, logging or not
+        if (rc != BNL_OK) break;
+        if (log) log_outer(log, outer_iter, ss, feas, mu, pix, omega, false);  // :293
     }
     if (log) fclose(log);
     if (rc != BNL_OK) return rc;

@@ -39,6 +39,9 @@ struct Scal {
     double c0;                 // built-in nonlinear constraint value c(x) (p = 1)
     int chol_fail;             // device Cholesky hit a non-positive pivot
     int p2p_timeout;           // peer-memory all-reduce gave up waiting for a rank
+    // persistent Cauchy breakpoint loop (cauchy_loop.cu)
+    int cl_status, cl_breakpoints;
+    long long cl_rounds;
 };
 
 // ---- block-wide deterministic reductions (fixed tree => run-to-run bit-identical) --------------------

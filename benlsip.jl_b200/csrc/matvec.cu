@@ -17,9 +17,12 @@
 // u + k*TG (k < KCH), keeps v and the J' accumulator for them in registers, reads its part of RB rows from
 // smem with conflict-free LDS.128, then the slot is released at once (the rows live in registers from here
 // on).  The RB row dot products are reduced with a transposing shuffle butterfly (warp teams: nothing else;
-// 256-thread team: + one named barrier); J'.t is accumulated from the same registers.  Per CTA the n column
-// sums (and sum t^2) go to partial[cta][*]; a second tiny kernel sums the partials in fixed CTA order =>
-// deterministic, no FP64 atomics.
+// 256-thread team: + one named barrier); J'.t is accumulated from the same registers.
+//
+// Row geometry (rowgeom.h): CTA b owns the chunks (g, b) of this rank's groups and walks them one after the other; the TMA
+// ring keeps running across chunk boundaries, but the accumulators are flushed to partial[g][b][team][*] at every chunk end,
+// so a partial only depends on chunk-local row indices.  group_reduce / group_sum (p2p.h) then add teams, chunks and groups
+// in one fixed tree => deterministic, no FP64 atomics, and bit-identical for 1, 2, 4 or 8 GPUs.
 //
 // Algorithmic bytes per launch (what roofline.achieved uses): 8*M_loc*ld (+ O(n)); J is read exactly once.
 #include "common.cuh"
@@ -99,12 +102,21 @@ __global__ void __launch_bounds__(kThreads, 1) mv_stream_kernel(const MvArgs a) 
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 2 * kMaxRB * 8);  // [NS]
 
     const int tid = threadIdx.x;
-    const long long total_stages = (a.M + RB - 1) / RB;
+    const int ng = a.geo.ng;
+    __shared__ long long s_cb[kGroups], s_ce[kGroups], s_nst[kGroups];  // chunk (gi, blockIdx.x): local rows, stages
+    __shared__ long long s_pst[kThreads / 32];                          // producer cursors (team leaders only)
+    __shared__ int s_pg[kThreads / 32];
 
     if (tid == 0) {
         for (int s = 0; s < a.NS; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid < ng) {
+        const long long cb = a.geo.local_begin(tid, blockIdx.x), ce = a.geo.local_end(tid, blockIdx.x);
+        s_cb[tid] = cb;
+        s_ce[tid] = ce;
+        s_nst[tid] = (ce - cb + RB - 1) / RB;
     }
     __syncthreads();
 
@@ -114,25 +126,33 @@ __global__ void __launch_bounds__(kThreads, 1) mv_stream_kernel(const MvArgs a) 
     const int warp = tid >> 5;
     double* my_stages = stages + (size_t)team * NSt * stage_doubles;
     uint64_t* my_full = full_bar + team * NSt;
-    // global stage index of this team's j-th stage: st(j) = blockIdx.x + (team + j*T) * gridDim.x
-    const long long st0 = blockIdx.x + (long long)team * gridDim.x;
-    const long long st_step = (long long)T * gridDim.x;
     uint64_t pol = 0;
 
-    auto issue = [&](long long j) {  // leader only: arm slot j % NSt with stage st(j)
-        const long long st = st0 + j * st_step;
-        if (st < total_stages) {
-            const int slot = (int)(j % NSt);
-            const long long row0 = st * RB;
-            const long long rows = (a.M - row0 < RB) ? (a.M - row0) : RB;
+    // leader only: arm `slot` with the team's next stage in (chunk, stage) order; the cursor lives in shared memory
+    auto issue_next = [&](int slot) {
+        int pg = s_pg[team];
+        long long pst = s_pst[team];
+        while (pg < ng && pst >= s_nst[pg]) {
+            ++pg;
+            pst = team;
+        }
+        if (pg < ng) {
+            const long long row0 = s_cb[pg] + pst * RB;
+            const long long left = s_ce[pg] - row0;
+            const long long rows = left < RB ? left : RB;
             const uint32_t bytes = (uint32_t)(rows * ld * sizeof(double));
             mbar_arrive_expect_tx(&my_full[slot], bytes);
             tma_bulk_g2s(my_stages + (size_t)slot * stage_doubles, a.J + row0 * ld, bytes, &my_full[slot], pol);
+            pst += T;
         }
+        s_pg[team] = pg;
+        s_pst[team] = pst;
     };
     if (u == 0) {
         pol = policy_evict_first();
-        for (int j = 0; j < NSt; ++j) issue(j);
+        s_pg[team] = 0;
+        s_pst[team] = team;
+        for (int j = 0; j < NSt; ++j) issue_next(j);
     }
 
     double2 vv[KCH];
@@ -140,148 +160,154 @@ __global__ void __launch_bounds__(kThreads, 1) mv_stream_kernel(const MvArgs a) 
 #pragma unroll
     for (int k = 0; k < KCH; ++k) {
         const int c = u + k * TG;
-        acc[k] = make_double2(0.0, 0.0);
         if (MODE != MODE_JTW)
             vv[k] = (c < NC) ? reinterpret_cast<const double2*>(a.v)[c] : make_double2(0.0, 0.0);
         else
             vv[k] = make_double2(0.0, 0.0);
     }
-    double tsq = 0.0;
     int batch_parity = 0;
+    int slot = 0;
+    uint32_t phase = 0;
 
-    long long j = 0;
-    for (long long st = st0; st < total_stages; st += st_step, ++j) {
-        const int slot = (int)(j % NSt);
-        const uint32_t use = (uint32_t)(j / NSt);
-        const long long row0 = st * RB;
-        const int rows_valid = (int)((a.M - row0 < RB) ? (a.M - row0) : RB);
-        mbar_wait(&my_full[slot], use & 1u);
-        const double2* sbase = reinterpret_cast<const double2*>(my_stages + (size_t)slot * stage_doubles);
+    for (int gi = 0; gi < ng; ++gi) {
+#pragma unroll
+        for (int k = 0; k < KCH; ++k) acc[k] = make_double2(0.0, 0.0);
+        double tsq = 0.0;
+        const long long cb = s_cb[gi], ce = s_ce[gi], nst = s_nst[gi];
+        for (long long st = team; st < nst; st += T) {
+            const long long row0 = cb + st * RB;
+            const int rows_valid = (int)((ce - row0 < RB) ? (ce - row0) : RB);
+            mbar_wait(&my_full[slot], phase);
+            const double2* sbase = reinterpret_cast<const double2*>(my_stages + (size_t)slot * stage_doubles);
 
-        double2 jr[RB][KCH];
-#pragma unroll
-        for (int q = 0; q < RB; ++q) {
-            const bool valid = q < rows_valid;
-#pragma unroll
-            for (int k = 0; k < KCH; ++k) {
-                const int c = u + k * TG;
-                jr[q][k] = (valid && c < NC) ? sbase[(size_t)q * NC + c] : make_double2(0.0, 0.0);
-            }
-        }
-
-        double t[RB];
-        if (MODE == MODE_JTW) {
-#pragma unroll
-            for (int q = 0; q < RB; ++q) t[q] = (q < rows_valid) ? __ldg(a.w + row0 + q) : 0.0;
-            // every thread of the team has issued its reads of the slot (in-order issue): re-arm it
-            if (WARP_TEAM)
-                __syncwarp();
-            else
-                named_bar_sync(1, kThreads);
-            if (u == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(j + NSt);
-            }
-        } else {
-            double part[RB];
+            double2 jr[RB][KCH];
 #pragma unroll
             for (int q = 0; q < RB; ++q) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // 4 independent FMA chains
+                const bool valid = q < rows_valid;
 #pragma unroll
                 for (int k = 0; k < KCH; ++k) {
-                    if (k & 1) {
-                        s2 = fma(jr[q][k].x, vv[k].x, s2);
-                        s3 = fma(jr[q][k].y, vv[k].y, s3);
-                    } else {
-                        s0 = fma(jr[q][k].x, vv[k].x, s0);
-                        s1 = fma(jr[q][k].y, vv[k].y, s1);
+                    const int c = u + k * TG;
+                    jr[q][k] = (valid && c < NC) ? sbase[(size_t)q * NC + c] : make_double2(0.0, 0.0);
+                }
+            }
+
+            double t[RB];
+            if (MODE == MODE_JTW) {
+#pragma unroll
+                for (int q = 0; q < RB; ++q) t[q] = (q < rows_valid) ? __ldg(a.w + row0 + q) : 0.0;
+                // every thread of the team has issued its reads of the slot (in-order issue): re-arm it
+                if (WARP_TEAM)
+                    __syncwarp();
+                else
+                    named_bar_sync(1, kThreads);
+                if (u == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue_next(slot);
+                }
+            } else {
+                double part[RB];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // 4 independent FMA chains
+#pragma unroll
+                    for (int k = 0; k < KCH; ++k) {
+                        if (k & 1) {
+                            s2 = fma(jr[q][k].x, vv[k].x, s2);
+                            s3 = fma(jr[q][k].y, vv[k].y, s3);
+                        } else {
+                            s0 = fma(jr[q][k].x, vv[k].x, s0);
+                            s1 = fma(jr[q][k].y, vv[k].y, s1);
+                        }
+                    }
+                    part[q] = (s0 + s1) + (s2 + s3);
+                }
+                if constexpr (WARP_TEAM) {
+                    // Re-arm the slot as early as safe: part[] depends on every J value this lane loaded (the empty asm pins
+                    // the re-arm below the FMAs that consumed them), and the warp barrier makes sure EVERY lane is past its
+                    // reads of the slot before the leader lets the bulk copy overwrite it (lanes may leave the mbarrier
+                    // spin loop on different iterations under independent thread scheduling).
+                    double dep = part[0];
+#pragma unroll
+                    for (int q = 1; q < RB; ++q) dep += part[q];
+                    asm volatile("" ::"d"(dep) : "memory");
+                    __syncwarp();
+                    if (u == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue_next(slot);
                     }
                 }
-                part[q] = (s0 + s1) + (s2 + s3);
-            }
-            if constexpr (WARP_TEAM) {
-                // Re-arm the slot as early as provably safe: part[] depends on every J value this lane loaded, the warp
-                // issues in order, and an LDS completes for all lanes at once => once the FMAs producing part[] have
-                // issued, every read of the slot has completed.  The empty asm pins the re-arm below those FMAs.
-                double dep = part[0];
+                // transposing butterfly: RB values x 32 lanes -> a lane holds one row's warp sum
+                double kx;
+                if constexpr (RB == 4) {  // 6 shuffles; lane holds row (2*bit4 + bit3)
+                    const bool hi16 = (lane & 16) != 0;
+                    double x0 = hi16 ? part[0] : part[2];
+                    double x1 = hi16 ? part[1] : part[3];
+                    double k0 = hi16 ? part[2] : part[0];
+                    double k1 = hi16 ? part[3] : part[1];
+                    k0 += __shfl_xor_sync(0xffffffffu, x0, 16);
+                    k1 += __shfl_xor_sync(0xffffffffu, x1, 16);
+                    const bool hi8 = (lane & 8) != 0;
+                    double sx = hi8 ? k0 : k1;
+                    kx = hi8 ? k1 : k0;
+                    kx += __shfl_xor_sync(0xffffffffu, sx, 8);
+                } else if constexpr (RB == 2) {  // 5 shuffles; lanes 0-15 -> row 0, lanes 16-31 -> row 1
+                    const bool hi16 = (lane & 16) != 0;
+                    double sx = hi16 ? part[0] : part[RB - 1];
+                    kx = hi16 ? part[RB - 1] : part[0];
+                    kx += __shfl_xor_sync(0xffffffffu, sx, 16);
+                    kx += __shfl_xor_sync(0xffffffffu, kx, 8);
+                } else {  // RB == 1: plain butterfly, every lane ends with the row sum
+                    kx = part[0];
+                    kx += __shfl_xor_sync(0xffffffffu, kx, 16);
+                    kx += __shfl_xor_sync(0xffffffffu, kx, 8);
+                }
+                kx += __shfl_xor_sync(0xffffffffu, kx, 4);
+                kx += __shfl_xor_sync(0xffffffffu, kx, 2);
+                kx += __shfl_xor_sync(0xffffffffu, kx, 1);
+                constexpr int LSH = (RB == 4) ? 3 : ((RB == 2) ? 4 : 5);  // row q's sum sits in lanes with (lane >> LSH) == q
+                if constexpr (WARP_TEAM) {
 #pragma unroll
-                for (int q = 1; q < RB; ++q) dep += part[q];
-                asm volatile("" ::"d"(dep) : "memory");
+                    for (int q = 0; q < RB; ++q) t[q] = __shfl_sync(0xffffffffu, kx, q << LSH);
+                } else {
+                    double* rbuf = red + batch_parity * (kMaxRB * 8);
+                    if ((lane & ((1 << LSH) - 1)) == 0 && (lane >> LSH) < RB) rbuf[(lane >> LSH) * 8 + warp] = kx;
+                    named_bar_sync(1, kThreads);
+                    if (u == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue_next(slot);
+                    }
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        const double* rq = rbuf + q * 8;
+                        t[q] = ((rq[0] + rq[1]) + (rq[2] + rq[3])) + ((rq[4] + rq[5]) + (rq[6] + rq[7]));
+                    }
+                    batch_parity ^= 1;
+                }
                 if (u == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(j + NSt);
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        tsq = fma(t[q], t[q], tsq);
+                        if (MODE == MODE_JV && a.t_out != nullptr && q < rows_valid) a.t_out[row0 + q] = t[q];
+                    }
                 }
             }
-            // transposing butterfly: RB values x 32 lanes -> a lane holds one row's warp sum
-            double kx;
-            if constexpr (RB == 4) {  // 6 shuffles; lane holds row (2*bit4 + bit3)
-                const bool hi16 = (lane & 16) != 0;
-                double x0 = hi16 ? part[0] : part[2];
-                double x1 = hi16 ? part[1] : part[3];
-                double k0 = hi16 ? part[2] : part[0];
-                double k1 = hi16 ? part[3] : part[1];
-                k0 += __shfl_xor_sync(0xffffffffu, x0, 16);
-                k1 += __shfl_xor_sync(0xffffffffu, x1, 16);
-                const bool hi8 = (lane & 8) != 0;
-                double sx = hi8 ? k0 : k1;
-                kx = hi8 ? k1 : k0;
-                kx += __shfl_xor_sync(0xffffffffu, sx, 8);
-            } else if constexpr (RB == 2) {  // 5 shuffles; lanes 0-15 -> row 0, lanes 16-31 -> row 1
-                const bool hi16 = (lane & 16) != 0;
-                double sx = hi16 ? part[0] : part[RB - 1];
-                kx = hi16 ? part[RB - 1] : part[0];
-                kx += __shfl_xor_sync(0xffffffffu, sx, 16);
-                kx += __shfl_xor_sync(0xffffffffu, kx, 8);
-            } else {  // RB == 1: plain butterfly, every lane ends with the row sum
-                kx = part[0];
-                kx += __shfl_xor_sync(0xffffffffu, kx, 16);
-                kx += __shfl_xor_sync(0xffffffffu, kx, 8);
-            }
-            kx += __shfl_xor_sync(0xffffffffu, kx, 4);
-            kx += __shfl_xor_sync(0xffffffffu, kx, 2);
-            kx += __shfl_xor_sync(0xffffffffu, kx, 1);
-            constexpr int LSH = (RB == 4) ? 3 : ((RB == 2) ? 4 : 5);  // row q's sum sits in lanes with (lane >> LSH) == q
-            if constexpr (WARP_TEAM) {
-#pragma unroll
-                for (int q = 0; q < RB; ++q) t[q] = __shfl_sync(0xffffffffu, kx, q << LSH);
-            } else {
-                double* rbuf = red + batch_parity * (kMaxRB * 8);
-                if ((lane & ((1 << LSH) - 1)) == 0 && (lane >> LSH) < RB) rbuf[(lane >> LSH) * 8 + warp] = kx;
-                named_bar_sync(1, kThreads);
-                if (u == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(j + NSt);
-                }
+            if (MODE != MODE_JV) {
 #pragma unroll
                 for (int q = 0; q < RB; ++q) {
-                    const double* rq = rbuf + q * 8;
-                    t[q] = ((rq[0] + rq[1]) + (rq[2] + rq[3])) + ((rq[4] + rq[5]) + (rq[6] + rq[7]));
-                }
-                batch_parity ^= 1;
-            }
-            if (u == 0) {
 #pragma unroll
-                for (int q = 0; q < RB; ++q) {
-                    tsq = fma(t[q], t[q], tsq);
-                    if (MODE == MODE_JV && a.t_out != nullptr && q < rows_valid) a.t_out[row0 + q] = t[q];
+                    for (int k = 0; k < KCH; ++k) {
+                        acc[k].x = fma(jr[q][k].x, t[q], acc[k].x);
+                        acc[k].y = fma(jr[q][k].y, t[q], acc[k].y);
+                    }
                 }
             }
-        }
-        if (MODE != MODE_JV) {
-#pragma unroll
-            for (int q = 0; q < RB; ++q) {
-#pragma unroll
-                for (int k = 0; k < KCH; ++k) {
-                    acc[k].x = fma(jr[q][k].x, t[q], acc[k].x);
-                    acc[k].y = fma(jr[q][k].y, t[q], acc[k].y);
-                }
+            if (++slot == NSt) {
+                slot = 0;
+                phase ^= 1u;
             }
         }
-    }
-
-    // ---- per-CTA result: combine teams in fixed order, write partial[cta][0..ld) (+ sum t^2 at [ld]) ----
-    double* pout = a.partial + (size_t)blockIdx.x * a.pstride;
-    if (T == 1) {
+        // ---- chunk end: flush this team's partial for chunk (gi, blockIdx.x): [0..ld) column sums, [ld] sum t^2 ----
+        double* pout = a.partial + (((size_t)gi * a.geo.G + blockIdx.x) * T + team) * a.pstride;
         if (MODE != MODE_JV) {
 #pragma unroll
             for (int k = 0; k < KCH; ++k) {
@@ -289,38 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) mv_stream_kernel(const MvArgs a) 
                 if (c < NC) reinterpret_cast<double2*>(pout)[c] = acc[k];
             }
         }
-        if (u == 0) pout[ld] = tsq;
-    } else {
-        // every armed stage was waited on by its team => all bulk copies have landed => the ring is reusable
-        __syncthreads();
-        double2* comb = reinterpret_cast<double2*>(stages);  // [T][NC] double2 (T*ld*8 bytes <= ring: NSt >= 1, RB >= 1)
-        double* tsq_s = red;                                 // [T]
-        if (MODE != MODE_JV) {
-#pragma unroll
-            for (int k = 0; k < KCH; ++k) {
-                const int c = u + k * TG;
-                if (c < NC) comb[(size_t)team * NC + c] = acc[k];
-            }
-        }
-        if (u == 0) tsq_s[team] = tsq;
-        __syncthreads();
-        if (MODE != MODE_JV) {
-            for (int c = tid; c < NC; c += kThreads) {
-                double2 s = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int gg = 0; gg < T; ++gg) {
-                    const double2 x = comb[(size_t)gg * NC + c];
-                    s.x += x.x;
-                    s.y += x.y;
-                }
-                reinterpret_cast<double2*>(pout)[c] = s;
-            }
-        }
-        if (tid == 0) {
-            double s = 0.0;
-            for (int gg = 0; gg < T; ++gg) s += tsq_s[gg];
-            pout[ld] = s;
-        }
+        if (MODE != MODE_JTW && u == 0) pout[ld] = tsq;
     }
 }
 
@@ -349,55 +344,10 @@ cudaError_t launch_mode(const MvArgs& a, int kch, int rb, bool warp_team, int gr
 #undef BNL_LAUNCH
 }
 
-// Sum partial[c][j] over CTAs c in fixed order.  One thread per column; columns [col0, ncols).
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nparts, long long pstride, int col0,
-                                       int ncols, double* __restrict__ out) {
-    const int j = col0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ncols) return;
-    double s = 0.0;
-    int c = 0;
-    for (; c + 4 <= nparts; c += 4) {
-        const double a0 = partial[(size_t)(c + 0) * pstride + j];
-        const double a1 = partial[(size_t)(c + 1) * pstride + j];
-        const double a2 = partial[(size_t)(c + 2) * pstride + j];
-        const double a3 = partial[(size_t)(c + 3) * pstride + j];
-        s += a0;
-        s += a1;
-        s += a2;
-        s += a3;
-    }
-    for (; c < nparts; ++c) s += partial[(size_t)c * pstride + j];
-    out[j] = s;
-}
-
-// reduce_partials_kernel + the push half of the peer-memory all-reduce in ONE kernel: the column sums of this rank
-// go straight into every peer's mailbox over NVLink (p2p.h); out is not written here (p2p_wait_sum does it).
-__global__ void reduce_push_kernel(const double* __restrict__ partial, int nparts, long long pstride, int col0, int ncols,
-                                   P2PArgs p2p, unsigned long long epoch) {
-    const int j = col0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < ncols) {
-        double s = 0.0;
-        int c = 0;
-        for (; c + 4 <= nparts; c += 4) {
-            const double a0 = partial[(size_t)(c + 0) * pstride + j];
-            const double a1 = partial[(size_t)(c + 1) * pstride + j];
-            const double a2 = partial[(size_t)(c + 2) * pstride + j];
-            const double a3 = partial[(size_t)(c + 3) * pstride + j];
-            s += a0;
-            s += a1;
-            s += a2;
-            s += a3;
-        }
-        for (; c < nparts; ++c) s += partial[(size_t)c * pstride + j];
-        p2p_push_value(p2p, epoch, j, s);
-    }
-    p2p_push_finish(p2p, epoch);
-}
-
 }  // namespace
 
 // ---- host-side planning ---------------------------------------------------------------------------------
-MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes) {
+MvPlan mv_make_plan(int n, size_t smem_optin_bytes) {
     MvPlan p{};
     p.ld = pad_cols(n);
     const int NC = p.ld / 2;
@@ -439,21 +389,17 @@ MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes) {
     if (ns < 2 * T) p.supported = false;
     p.NS = ns;
     p.smem_bytes = (size_t)ns * stage_bytes + 2 * kMaxRB * 8 * sizeof(double) + (size_t)ns * sizeof(uint64_t);
-    long long total_stages = (M + p.R - 1) / p.R;
-    long long grid = total_stages < sm_count ? total_stages : sm_count;
-    if (grid < 1) grid = 1;
-    p.grid = (int)grid;
+    p.T = T;
     p.pstride = p.ld + kColAlign;
     return p;
 }
 
-cudaError_t mv_launch(int mode, const MvPlan& p, const double* J, long long M, const double* v, const double* w,
-                      double* t_out, double* partial, double* out, cudaStream_t stream, const P2PArgs* p2p,
-                      unsigned long long epoch) {
+cudaError_t mv_launch(int mode, const MvPlan& p, const RowGeom& geo, const double* J, const double* v, const double* w,
+                      double* t_out, double* partial, cudaStream_t stream) {
     if (!p.supported) return cudaErrorInvalidValue;
     MvArgs a{};
     a.J = J;
-    a.M = M;
+    a.geo = geo;
     a.ld = p.ld;
     a.R = p.R;
     a.NS = p.NS;
@@ -463,25 +409,12 @@ cudaError_t mv_launch(int mode, const MvPlan& p, const double* J, long long M, c
     a.t_out = t_out;
     a.partial = partial;
     a.pstride = p.pstride;
-    cudaError_t e;
     switch (mode) {
-        case MODE_JTJV: e = launch_mode<MODE_JTJV>(a, p.KCH, p.RB, p.warp_team, p.grid, p.smem_bytes, stream); break;
-        case MODE_JV: e = launch_mode<MODE_JV>(a, p.KCH, p.RB, p.warp_team, p.grid, p.smem_bytes, stream); break;
-        case MODE_JTW: e = launch_mode<MODE_JTW>(a, p.KCH, p.RB, p.warp_team, p.grid, p.smem_bytes, stream); break;
-        default: return cudaErrorInvalidValue;
+        case MODE_JTJV: return launch_mode<MODE_JTJV>(a, p.KCH, p.RB, p.warp_team, geo.G, p.smem_bytes, stream);
+        case MODE_JV: return launch_mode<MODE_JV>(a, p.KCH, p.RB, p.warp_team, geo.G, p.smem_bytes, stream);
+        case MODE_JTW: return launch_mode<MODE_JTW>(a, p.KCH, p.RB, p.warp_team, geo.G, p.smem_bytes, stream);
     }
-    if (e != cudaSuccess) return e;
-    const int ncols = p.ld + 1;
-    const int col0 = (mode == MODE_JV) ? p.ld : 0;  // JV only produces the sum-of-squares slot
-    if (p2p != nullptr) {
-        // fused local reduce + NVLink push; then wait for all ranks and sum in rank order (bit-identical everywhere)
-        reduce_push_kernel<<<(ncols - col0 + 127) / 128, 128, 0, stream>>>(partial, p.grid, p.pstride, col0, ncols, *p2p, epoch);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        return p2p_wait_sum(*p2p, epoch, out, col0, ncols, stream);
-    }
-    reduce_partials_kernel<<<(ncols - col0 + 127) / 128, 128, 0, stream>>>(partial, p.grid, p.pstride, col0, ncols, out);
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace bnl

@@ -3,37 +3,39 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "p2p.h"
+#include "rowgeom.h"
+
 namespace bnl {
 
 enum { MODE_JTJV = 0, MODE_JV = 1, MODE_JTW = 2 };
 
 struct MvArgs {
-    const double* J;   // row-major M x ld
-    long long M;       // local rows
+    const double* J;   // row-major M_loc x ld
+    RowGeom geo;       // chunk geometry: CTA b owns the chunks (g, b) of the local groups
     int ld, R, NS, TG;
     const double* v;   // length ld (zero padded)      [JTJV, JV]
-    const double* w;   // length M                     [JTW]
-    double* t_out;     // length M or null             [JV]
-    double* partial;   // [grid][pstride]
+    const double* w;   // length M_loc                 [JTW]
+    double* t_out;     // length M_loc or null         [JV]
+    double* partial;   // [ng][G][T][pstride]
     long long pstride;
 };
 
 struct MvPlan {
-    int ld, TG, KCH, RB, R, NS, grid;
+    int ld, TG, T, KCH, RB, R, NS;
     long long pstride;
     size_t smem_bytes;
     bool supported;
     bool warp_team;
 };
 
-MvPlan mv_make_plan(long long M, int n, int sm_count, size_t smem_optin_bytes);
+MvPlan mv_make_plan(int n, size_t smem_optin_bytes);
+inline size_t mv_partial_doubles(const MvPlan& p, const RowGeom& geo) { return (size_t)geo.ng * geo.G * p.T * p.pstride; }
 
-// Launches the streaming kernel + the fixed-order partial reduction on `stream`.
-// out: length ld+1 doubles; out[0..ld) = J'(Jv) or J'w, out[ld] = sum (Jv)_i^2 (JTJV, JV modes).
-// p2p != nullptr: the partial reduction also pushes to every peer's mailbox and `out` holds the ALL-REDUCED result.
-struct P2PArgs;
-cudaError_t mv_launch(int mode, const MvPlan& p, const double* J, long long M, const double* v, const double* w,
-                      double* t_out, double* partial, double* out, cudaStream_t stream, const P2PArgs* p2p = nullptr,
-                      unsigned long long epoch = 0);
+// Launches the streaming kernel (grid = geo.G CTAs) on `stream`.  It leaves one partial per (chunk, team) in
+// partial[ng][G][T][pstride]: [0..ld) = column sums of J'(Jv) / J'w, [ld] = sum (Jv)_i^2 (JTJV, JV).  The caller finishes with
+// the fixed reduction tree (group_reduce + group_sum, p2p.h): columns [0, ld] for JTJV, [ld, ld] for JV, [0, ld) for JTW.
+cudaError_t mv_launch(int mode, const MvPlan& p, const RowGeom& geo, const double* J, const double* v, const double* w,
+                      double* t_out, double* partial, cudaStream_t stream);
 
 }  // namespace bnl

@@ -36,10 +36,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) glm_kernel(ModelArgs a, con
                                                                 double* __restrict__ J, double* __restrict__ partial) {
     __shared__ double shd[32];
     const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const long long nw = (long long)gridDim.x * kWarpsPerCta;
+    // WHAT == 1 carries a row reduction (sum r_i^2): CTA (gi, b) owns one row chunk and a warp takes every 8th row of it, so
+    // the partial only depends on chunk-local indices (rowgeom.h).  The element-wise kernels stride over all local rows.
+    long long i0, i1, istep;
+    if (WHAT == 1) {
+        const int cg = blockIdx.x / a.geo.G, cb = blockIdx.x % a.geo.G;
+        i0 = a.geo.local_begin(cg, cb) + (threadIdx.x >> 5);
+        i1 = a.geo.local_end(cg, cb);
+        istep = kWarpsPerCta;
+    } else {
+        i0 = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+        i1 = a.M;
+        istep = (long long)gridDim.x * kWarpsPerCta;
+    }
     double ss = 0.0;
-    for (long long i = gw; i < a.M; i += nw) {
+    for (long long i = i0; i < i1; i += istep) {
         const unsigned long long gi = (unsigned long long)(a.row0 + i);
         const uint32_t rk = rowkey(a.seed, gi);
         const double z = glm_row_dot(a, rk, x, lane);
@@ -83,8 +94,18 @@ __global__ void expsum_rows_kernel(ModelArgs a, const double* __restrict__ x, co
     __shared__ double shd[32];
     const int C = a.n / 2;
     double ss = 0.0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.M; i += stride) {
+    long long i0, i1, stride;
+    if (WHAT == 1) {  // one row chunk per CTA (rowgeom.h)
+        const int cg = blockIdx.x / a.geo.G, cb = blockIdx.x % a.geo.G;
+        i0 = a.geo.local_begin(cg, cb) + threadIdx.x;
+        i1 = a.geo.local_end(cg, cb);
+        stride = blockDim.x;
+    } else {
+        i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        i1 = a.M;
+        stride = (long long)gridDim.x * blockDim.x;
+    }
+    for (long long i = i0; i < i1; i += stride) {
         const long long gi = a.row0 + i;
         const int c = (int)(gi % C);
         const double t = expsum_t(a, gi, C);
@@ -127,14 +148,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) expsum_jac_kernel(ModelArgs
     }
 }
 
-__global__ void sum_partials_kernel(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
-    __shared__ double shd[32];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
-    s = block_sum(s, shd);
-    if (threadIdx.x == 0) out[0] = s;
-}
-
 int rows_grid(long long M, int nblocks_cap) {
     long long g = (M + kWarpsPerCta - 1) / kWarpsPerCta;
     if (g > nblocks_cap) g = nblocks_cap;
@@ -155,19 +168,15 @@ cudaError_t model_setup_y(const ModelArgs& a, const double* x_true, double* y, c
     return cudaGetLastError();
 }
 
-cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y, double* r, double* partial,
-                           int nblocks, double* sumsq_out, cudaStream_t st) {
-    int grid;
+cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y, double* r, double* partial, cudaStream_t st) {
+    const int grid = a.geo.ng * a.geo.G;  // one CTA per row chunk; partial[grid] goes through the fixed reduction tree (p2p.h)
     if (a.model_id == 1) {
-        grid = rows_grid(a.M, nblocks);
         glm_kernel<1><<<grid, kWarpsPerCta * 32, 0, st>>>(a, x, y, r, nullptr, partial);
     } else if (a.model_id == 2) {
-        grid = rows_grid(a.M / 32 + 1, nblocks);
         expsum_rows_kernel<1><<<grid, 256, 0, st>>>(a, x, y, r, partial);
     } else {
         return cudaErrorInvalidValue;
     }
-    sum_partials_kernel<<<1, 256, 0, st>>>(partial, grid, sumsq_out);
     return cudaGetLastError();
 }
 

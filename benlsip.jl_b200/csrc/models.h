@@ -3,11 +3,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "rowgeom.h"
+
 namespace bnl {
 
 struct ModelArgs {
     int model_id;
     long long M, M_total, row0;
+    RowGeom geo;       // row-chunk geometry of the reductions (residual sum of squares)
     int n, ld;
     uint32_t seed;
     double noise;
@@ -16,9 +19,8 @@ struct ModelArgs {
 
 // y = model(x_true) + noise  (once, at bind time)
 cudaError_t model_setup_y(const ModelArgs& a, const double* x_true, double* y, cudaStream_t st);
-// r = model(x) - y ; sumsq_out[0] = sum r_i^2 over local rows (fixed-order two-stage reduction)
-cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y, double* r, double* partial,
-                           int nblocks, double* sumsq_out, cudaStream_t st);
+// r = model(x) - y ; partial[gi*G + b] = sum r_i^2 over the row chunk (gi, b) (rowgeom.h)
+cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y, double* r, double* partial, cudaStream_t st);
 // J (row-major M x ld, zero padded) = d model / d x at x
 cudaError_t model_jacobian(const ModelArgs& a, const double* x, double* J, cudaStream_t st);
 

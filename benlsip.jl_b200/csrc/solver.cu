@@ -14,7 +14,7 @@ namespace bnl_host {
 int sync(S* h) {
     if (h->p2p_on) vk_publish(h->sd, h->sh, h->stream);  // make a peer-wait timeout visible even when no O(n) kernel followed
     CK(cudaStreamSynchronize(h->stream));
-    if (h->p2p_on && h->sh->p2p_timeout) return h->fail(BNL_ENCCL, "peer-memory all-reduce timed out waiting for a rank");
+    if (h->p2p_on && h->sh->p2p_timeout) return h->fail(BNL_ENCCL, "peer-memory exchange timed out waiting for a rank");
     // harvest finished event pairs
     for (size_t i = 0; i < h->ev_busy.size();) {
         EvPair& e = h->ev_busy[i];
@@ -83,18 +83,41 @@ int get_vec(S* h, const double* src_dev, double* dst, size_t count) {
     return BNL_OK;
 }
 
+// NCCL all-reduce: only the n^2 Gram (opt-in mode) still uses it; every reduction of the default path goes through row_reduce.
 int allreduce(S* h, double* buf, size_t count) {
     if (h->nranks <= 1) return BNL_OK;
-    if (h->p2p_on && count <= (size_t)kP2PWidth) {
-        CK(p2p_allreduce(h->p2p, ++h->p2p_epoch, buf, (int)count, h->stream));
-        h->st.kernel_launches += 2;
-        h->st.allreduces++;
-        h->st.p2p_allreduces++;
-        return BNL_OK;
-    }
+    if (!h->comm) return h->fail(BNL_ENCCL, "no NCCL communicator (bnl_comm_init)");
     ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess) return h->fail(BNL_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     h->st.allreduces++;
+    return BNL_OK;
+}
+
+// The fixed reduction tree of rowgeom.h: teams -> chunks -> groups (this rank's groups), exchange of the group sums with the
+// peers (NVLink stores into every rank's mailbox, or ncclAllGather when peers cannot be mapped), then the 8 group sums in
+// order.  Bit-identical on every rank and for N = 1, 2, 4, 8.
+int row_reduce(S* h, const double* P, int T, long long pstride, int col0, int ncols, double* out) {
+    const unsigned long long epoch = ++h->p2p_epoch;
+    const RowGeom& g = h->geo;
+    if (h->nranks <= 1) {
+        CK(group_reduce(P, g.G, T, pstride, col0, ncols, g.g0, g.ng, h->p2p, epoch, GR_LOCAL, h->stream));
+        CK(group_sum(h->p2p, epoch, out, col0, ncols, 0, h->stream));
+    } else if (h->p2p_on) {
+        CK(group_reduce(P, g.G, T, pstride, col0, ncols, g.g0, g.ng, h->p2p, epoch, GR_PUSH, h->stream));
+        CK(group_sum(h->p2p, epoch, out, col0, ncols, 1, h->stream));
+        h->st.allreduces++;
+        h->st.p2p_allreduces++;
+    } else {
+        CK(group_reduce(P, g.G, T, pstride, col0, ncols, g.g0, g.ng, h->p2p, epoch, GR_LOCAL, h->stream));
+        double* region = h->p2p_buf + (size_t)(epoch & 1ull) * kGroups * kP2PWidth;  // [kGroups][kP2PWidth]: rank r owns rows [r*ng, (r+1)*ng)
+        const size_t cnt = (size_t)g.ng * kP2PWidth;
+        if (!h->comm || !g_nccl.AllGather) return h->fail(BNL_ENCCL, "no NCCL communicator (bnl_comm_init)");
+        ncclResult_t r = g_nccl.AllGather(region + (size_t)g.g0 * kP2PWidth, region, cnt, ncclDouble, h->comm, h->stream);
+        if (r != ncclSuccess) return h->fail(BNL_ENCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        CK(group_sum(h->p2p, epoch, out, col0, ncols, 0, h->stream));
+        h->st.allreduces++;
+    }
+    h->st.kernel_launches += 2;
     return BNL_OK;
 }
 
@@ -128,20 +151,13 @@ int hess_mul(S* h, const double* dv, double* out) {
         CK(gram_apply(h->gram, h->n, h->ld, dv, out, h->stream));
         h->st.kernel_launches += 2;
     } else {
-        const bool fused = h->p2p_on;  // reduce + NVLink push in one kernel, then wait+sum
         {
             EvScope ev(h, 0);
-            CK(mv_launch(MODE_JTJV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, out, h->stream,
-                         fused ? &h->p2p : nullptr, fused ? ++h->p2p_epoch : 0));
+            CK(mv_launch(MODE_JTJV, h->plan, h->geo, h->J, dv, nullptr, nullptr, h->partial, h->stream));
         }
-        h->st.kernel_launches += fused ? 3 : 2;
+        KLAUNCH();
         h->st.j_passes += 1;
-        if (fused) {
-            h->st.allreduces++;
-            h->st.p2p_allreduces++;
-        } else {
-            RET(allreduce(h, out, (size_t)h->ld + 1));
-        }
+        RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, 0, h->ld + 1, out));
     }
     if (h->p > 0) {
         vk_hess_c(h->vc, dv, out, true, h->stream);
@@ -163,20 +179,13 @@ int vthv_dev(S* h, const double* dv) {
         CK(cudaMemcpyAsync(h->vc.hv + h->ld, h->vc.t1 + h->ld, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         h->st.kernel_launches += 2;
     } else {
-        const bool fused = h->p2p_on;
         {
             EvScope ev(h, 1);
-            CK(mv_launch(MODE_JV, h->plan, h->J, h->M, dv, nullptr, nullptr, h->partial, h->vc.hv, h->stream,
-                         fused ? &h->p2p : nullptr, fused ? ++h->p2p_epoch : 0));
+            CK(mv_launch(MODE_JV, h->plan, h->geo, h->J, dv, nullptr, nullptr, h->partial, h->stream));
         }
-        h->st.kernel_launches += fused ? 3 : 2;
+        KLAUNCH();
         h->st.j_passes += 1;
-        if (fused) {
-            h->st.allreduces++;
-            h->st.p2p_allreduces++;
-        } else {
-            RET(allreduce(h, h->vc.hv + h->ld, 1));
-        }
+        RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, h->ld, h->ld + 1, h->vc.hv));
     }
     if (h->p > 0) {
         vk_hess_c(h->vc, dv, nullptr, false, h->stream);
@@ -190,20 +199,13 @@ int vthv_dev(S* h, const double* dv) {
 // J' w  (w: device, local rows) -> out (length ld+1), all-reduced
 int jtw_dev(S* h, const double* dw, double* out) {
     if (!h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
-    const bool fused = h->p2p_on;
     {
         EvScope ev(h, 2);
-        CK(mv_launch(MODE_JTW, h->plan, h->J, h->M, nullptr, dw, nullptr, h->partial, out, h->stream,
-                     fused ? &h->p2p : nullptr, fused ? ++h->p2p_epoch : 0));
+        CK(mv_launch(MODE_JTW, h->plan, h->geo, h->J, nullptr, dw, nullptr, h->partial, h->stream));
     }
-    h->st.kernel_launches += fused ? 3 : 2;
+    KLAUNCH();
     h->st.j_passes += 1;
-    if (fused) {
-        h->st.allreduces++;
-        h->st.p2p_allreduces++;
-    } else {
-        RET(allreduce(h, out, (size_t)h->ld));
-    }
+    RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, 0, h->ld, out));
     h->st.jtw++;
     return BNL_OK;
 }
@@ -243,6 +245,7 @@ ModelArgs margs(S* h) {
     a.M = h->M;
     a.M_total = h->M_total;
     a.row0 = h->row0;
+    a.geo = h->geo;
     a.n = h->n;
     a.ld = h->ld;
     a.seed = h->seed;
@@ -257,8 +260,8 @@ int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_o
     c_out.assign(h->p, 0.0);
     if (h->model_id != 0) {
         EvScope ev(h, 3);
-        CK(model_residual(margs(h), dx, h->ydata, rbuf, h->sumsq_partial, h->sumsq_blocks, &h->sd->sumsq_r, h->stream));
-        h->st.kernel_launches += 2;
+        CK(model_residual(margs(h), dx, h->ydata, rbuf, h->rpartial, h->stream));
+        KLAUNCH();
         if (h->p > 0) {  // built-in nlconstraints(x): the p-vector lives on the host, like the reference's closure result
             if (h->nl_kind != BNL_NLCONS_SPHERE) return h->fail(BNL_EINVAL, "p > 0 with a built-in model needs bnl_use_builtin_nlcons");
             vk_sphere_value(h->vc, dx, h->nl_rho2, h->stream);
@@ -274,14 +277,14 @@ int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_o
         if (h->cb_res(h->h_x.data(), h->pin, h->cb_ctx) != 0) return h->fail(BNL_ECALLBACK, "residuals callback failed");
         CK(cudaMemcpyAsync(rbuf, h->pin, (size_t)h->M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        vk_sumsq(rbuf, h->M, h->sumsq_partial, h->sumsq_blocks, &h->sd->sumsq_r, h->stream);
-        h->st.kernel_launches += 2;
+        vk_sumsq_chunks(rbuf, h->geo, h->rpartial, h->stream);
+        KLAUNCH();
         if (h->p > 0) {
             if (!h->cb_nl) return h->fail(BNL_EINVAL, "p > 0 but no nlconstraints callback");
             if (h->cb_nl(h->h_x.data(), c_out.data(), h->cb_ctx) != 0) return h->fail(BNL_ECALLBACK, "nlconstraints callback failed");
         }
     }
-    RET(allreduce(h, &h->sd->sumsq_r, 1));
+    RET(row_reduce(h, h->rpartial, 1, 1, 0, 1, &h->sd->sumsq_r));  // dot(rx,rx) over all ranks' rows
     h->st.res_eval++;
     return BNL_OK;
 }
@@ -389,61 +392,71 @@ double al_value(S* h, double sumsq, const std::vector<double>& y, const std::vec
     return 0.5 * sumsq + yc + 0.5 * mu * cc;
 }
 
-// ---- cauchy_step :574-639, incremental form (opt-in, bound-only problems) -----------------------------------------
-// Same search, same decisions; the two scalars it needs per interval are maintained from t = J d and u = J s_c instead
-// of a fresh Hd = H*d per breakpoint (:633): one strided column of J + two M-vector streams instead of a pass over J.
+// ---- cauchy_step :574-639 with the breakpoint loop on the device (cauchy_loop.cu) ---------------------------------
+// t = J d once (one pass), then ONE persistent kernel walks the breakpoints; whenever a number that reaches the iterate is
+// needed (interior minimiser) or a decision is inside the rounding band, Hd = H*d is evaluated literally (:633-635) and
+// the loop is re-entered with those values => the Cauchy point equals the literal search's bit for bit.
 int cauchy_step_incremental(S* h, double delta) {
     VecCtx& c = h->vc;
     if (!h->inc_t) {
         const size_t mb = std::max<size_t>(h->M, 16) * sizeof(double);
         CK(cudaMalloc(&h->inc_t, mb));
         CK(cudaMalloc(&h->inc_u, mb));
-        CK(cudaMalloc(&h->inc_partial, 2 * (size_t)h->inc_blocks * sizeof(double)));
-        CK(cudaMalloc(&h->inc_out2, 16 * sizeof(double)));
+        CK(cudaMalloc(&h->cl_sync, cauchy_loop_sync_bytes()));
     }
     vk_active_reset(c, c.x, nullptr, h->stream);  // :591
     vk_cauchy_init(c, true, h->stream);           // s_c = 0 ; d = P(-g) :592
     h->st.kernel_launches += 2;
-    {   // t = J d  (one J pass; ||t||^2 is recomputed below together with u.t = 0)
+    {   // t = J d  (one J pass; the loop computes ||t||^2 itself, in the chunk geometry)
         EvScope ev(h, 1);
-        CK(mv_launch(MODE_JV, h->plan, h->J, h->M, c.d, nullptr, h->inc_t, h->partial, c.hv, h->stream));
+        CK(mv_launch(MODE_JV, h->plan, h->geo, h->J, c.d, nullptr, h->inc_t, h->partial, h->stream));
     }
-    h->st.kernel_launches += 2;
+    KLAUNCH();
     h->st.j_passes += 1;
     h->st.jv++;
-    auto scalars = [&](int first) -> int {
-        vk_cauchy_inc(c, h->J, h->M, h->inc_t, h->inc_u, h->inc_partial, h->inc_blocks, first, h->stream);
-        vk_cauchy_inc_reduce(h->inc_partial, h->inc_blocks, h->inc_out2, h->stream);
-        h->st.kernel_launches += 2;
-        RET(allreduce(h, h->inc_out2, 2));
-        vk_cauchy_eval_inc(c, delta, h->inc_out2, h->stream);
-        KLAUNCH();
-        return sync(h);
-    };
-    RET(scalars(1));
-    bool min_found = false;
-    const int nmm = h->n - h->m_lin;
-    while (!min_found && h->sh->nb_fix < nmm) {  // :615
-        const double phi_p = h->sh->phi_p, phi_pp = h->sh->phi_pp, theta = h->sh->theta;
-        const double delta_t = (phi_pp > 0) ? -phi_p / phi_pp : 0.0;
-        if (phi_p >= 0) {
-            min_found = true;
-        } else if (phi_p < 0 && phi_pp > 0 && delta_t < theta) {
-            vk_cauchy_advance(c, true, 0, h->stream);
-            KLAUNCH();
-            min_found = true;
-        } else {
-            if (h->sh->bp_ind < 0) return h->fail(BNL_EBOUNDS, "BoundsError: next_breakpoint found no breakpoint (ind = -1)");
-            // the M-vector update reads theta / ind / d[ind] of THIS scan from the device scalars, so it must be queued
-            // before the advance kernel overwrites nothing it needs (advance only touches s, fix, d, nb_fix)
-            vk_cauchy_advance(c, true, 1, h->stream);
-            KLAUNCH();
-            RET(scalars(0));
-            h->st.breakpoints++;
-            h->st.inc_breakpoints++;
+    CauchyLoopArgs a{};
+    a.c = c;
+    a.geo = h->geo;
+    a.J = h->J;
+    a.ld = h->ld;
+    a.t = h->inc_t;
+    a.u = h->inc_u;
+    a.partial2 = h->rpartial;
+    a.p2p = h->p2p;
+    a.multi = h->nranks > 1 ? 1 : 0;
+    a.delta = delta;
+    a.guard = h->cauchy_guard;
+    a.nmm = h->n - h->m_lin;
+    a.arrive = h->cl_sync;
+    a.bcast = reinterpret_cast<char*>(h->cl_sync) + 64;
+    a.first = 1;
+    a.use_literal = 0;
+    for (;;) {
+        a.ll_epoch0 = h->ll_epoch;
+        CK(cauchy_loop_launch(a, h->prop.multiProcessorCount, h->stream));
+        h->st.kernel_launches++;
+        h->st.cauchy_loop_launches++;
+        RET(sync(h));
+        h->ll_epoch += (unsigned long long)h->sh->cl_rounds;
+        h->st.breakpoints += h->sh->cl_breakpoints;
+        h->st.inc_breakpoints += h->sh->cl_breakpoints;
+        switch (h->sh->cl_status) {
+            case CL_DONE_NOSTEP:
+            case CL_DONE_INTERIOR:
+            case CL_DONE_EXHAUSTED: return BNL_OK;
+            case CL_NEED_LITERAL:
+                RET(hess_mul(h, c.d, c.hv));          // :609 / :633
+                vk_cauchy_eval(c, delta, h->stream);  // :610-611 / :634-635 -> sd->phi_p, sd->phi_pp
+                KLAUNCH();
+                h->st.cauchy_literal_evals++;
+                a.first = 0;
+                a.use_literal = 1;
+                break;
+            case CL_ERR_BOUNDS: return h->fail(BNL_EBOUNDS, "BoundsError: next_breakpoint found no breakpoint (ind = -1)");
+            case CL_TIMEOUT: return h->fail(BNL_ENCCL, "peer-memory exchange timed out waiting for a rank (Cauchy loop)");
+            default: return h->fail(BNL_ECUDA, "cauchy loop: unexpected status %d", h->sh->cl_status);
         }
     }
-    return BNL_OK;
 }
 
 // ---- cauchy_step :574-639 --------------------------------------------------------------------------------
@@ -500,10 +513,10 @@ int nrg_general(S* h) {
 }
 
 // ---- minor_iterate :649-675 with projected_cg :690-764 and linesearch :766-791 ---------------------------
-int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool apply_linesearch_and_accumulate) {
+int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool apply_linesearch_and_accumulate, bool bounds_given) {
     VecCtx& c = h->vc;
     if (!h->mask) RET(project_general(h, c.gm, c.v, false));  // v = projection(lincons, r), r = g_minor :706
-    vk_cg_init(c, h->mask, delta, h->stream);
+    vk_cg_init(c, h->mask, delta, bounds_given, h->stream);
     KLAUNCH();
     RET(sync(h));
     const int max_iter = 2 * (h->n - h->m_lin - h->sh->nb_fix);  // :714
@@ -553,7 +566,9 @@ int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool appl
 // ---- inner_step :394-460 ---------------------------------------------------------------------------------
 int inner_step(S* h, double delta, double* pred_out) {
     VecCtx& c = h->vc;
-    if (h->cauchy_mode == BNL_CAUCHY_INCREMENTAL && h->mask)
+    // bound-only problems (mask projection; the loop carries up to kCLMaxP nonlinear-constraint rows itself): device-side
+    // breakpoint loop; everything else, and Gram mode (where H*d is an L2-resident gemv anyway): the literal search
+    if (h->cauchy_mode == BNL_CAUCHY_INCREMENTAL && h->mask && h->p <= kCLMaxP && h->hess_mode == BNL_HESSIAN_MATRIX_FREE)
         RET(cauchy_step_incremental(h, delta));
     else
         RET(cauchy_step(h, delta));  // :410
@@ -569,7 +584,7 @@ int inner_step(S* h, double delta, double* pred_out) {
     int j = 1;
     while (j <= max_minor && !approx_solved && !cg_stop) {  // :430
         int status = 0;
-        RET(minor_iterate(h, delta, &status, nullptr, true));  // :434-436
+        RET(minor_iterate(h, delta, &status, nullptr, true, false));  // :434-436
         cg_stop = (status == BNL_CG_NEGATIVE_CURVATURE);
         RET(hess_mul(h, c.s, c.hv));  // :437
         vk_minor_post(c, h->mask, delta, h->stream);
@@ -592,7 +607,11 @@ int inner_step(S* h, double delta, double* pred_out) {
         ++j;
         h->st.minor_iters++;
     }
-    RET(vthv_dev(h, c.s));  // :458
+    // vthv(H,s) :458 = ||J s||^2 + mu ||C s||^2.  The last Hessian apply above was H*s of this very s (:412 / :437): the fused
+    // kernel left ||J s||^2 in hv[ld] (same per-row arithmetic and reduction tree as the J*v-only mode) and k_hess_c left
+    // ||C s||^2, so the reference's extra pass over J is not repeated.
+    h->st.vthv++;
+    h->st.jv++;
     vk_dot_gs(c, h->stream);
     KLAUNCH();
     RET(sync(h));
@@ -663,7 +682,16 @@ int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double o
         rec.delta = delta;
         rec.rho = rho;
         rec.pred = pred;
-        if (log) fprintf(log, "%4d   %.6e   %.2e   %.2e   %.2e\n", k, mx, rec.norm_s, delta, rho);  // misc.jl:70-80
+        if (log) {  // print_inner_iter, misc.jl:70-80 (Julia's Printf spells non-finite values NaN / Inf)
+            auto e = [](int prec, double v) -> std::string {
+                if (std::isnan(v)) return "NaN";
+                if (std::isinf(v)) return v > 0 ? "Inf" : "-Inf";
+                char buf[64];
+                snprintf(buf, sizeof buf, "%.*e", prec, v);
+                return buf;
+            };
+            fprintf(log, "%4d   %s   %s   %s   %s\n", k, e(6, mx).c_str(), e(2, rec.norm_s).c_str(), e(2, delta).c_str(), e(2, rho).c_str());
+        }
         if (rho > h->prm.eta1) {  // :358-363
             CK(cudaMemcpyAsync(c.x, c.xn, (size_t)h->ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
             std::swap(h->r, h->r_trial);
@@ -700,6 +728,54 @@ int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double o
     return BNL_OK;
 }
 
+void p2p_local_setup(S* h) {
+    h->p2p = P2PArgs{};
+    h->p2p.nranks = 1;
+    h->p2p.rank = 0;
+    h->p2p.mbox[0] = h->p2p_buf;
+    h->p2p.flag[0] = p2p_flags_of(h->p2p_buf);
+    h->p2p.ll[0] = p2p_ll_of(h->p2p_buf);
+    h->p2p.done_counter = h->p2p_counter;
+    h->p2p.timeout_flag = &h->sd->p2p_timeout;
+}
+
+// The row-chunk geometry of this handle (rowgeom.h).  After bnl_comm_init it follows (nranks, rank) and the caller's rows
+// must be exactly that rank's shard (bnl_shard_rows); before, it is inferred from (row0, M_local): the largest whole-group
+// range that matches (a single-GPU problem owns all 8 groups).
+int resolve_geometry(S* h) {
+    RowGeom g{};
+    if (h->comm_set) {
+        if (!geom_make(h->M_total, h->nranks, h->rank, &g)) return h->fail(BNL_EINVAL, "bad (nranks, rank)");
+        if (g.row0 != h->row0 || g.local_rows() != h->M)
+            return h->fail(BNL_EDIM, "DimensionMismatch: rows [%lld, %lld) are not the shard of rank %d of %d (use bnl_shard_rows: [%lld, %lld))",
+                           h->row0, h->row0 + h->M, h->rank, h->nranks, g.row0, g.row0 + g.local_rows());
+    } else {
+        bool found = false;
+        for (int nr = 1; nr <= kGroups && !found; nr <<= 1)
+            for (int r = 0; r < nr && !found; ++r)
+                found = geom_make(h->M_total, nr, r, &g) && g.row0 == h->row0 && g.local_rows() == h->M;
+        if (!found)
+            return h->fail(BNL_EDIM, "DimensionMismatch: rows [%lld, %lld) of %lld are not a whole-group shard (use bnl_shard_rows)", h->row0,
+                           h->row0 + h->M, h->M_total);
+    }
+    h->geo = g;
+    return BNL_OK;
+}
+
+int alloc_row_buffers(S* h) {
+    cudaFree(h->partial);
+    cudaFree(h->rpartial);
+    h->partial = h->rpartial = nullptr;
+    const size_t np = std::max<size_t>(mv_partial_doubles(h->plan, h->geo), 16);
+    CK(cudaMalloc(&h->partial, np * sizeof(double)));
+    CK(cudaMemset(h->partial, 0, np * sizeof(double)));
+    CK(cudaMalloc(&h->rpartial, std::max<size_t>((size_t)h->geo.ng * h->geo.G * 4, 16) * sizeof(double)));
+    // a handle that owns only some groups and has no peers (a shard examined on its own): the other groups' mailbox rows
+    // must read as zero
+    if (h->nranks <= 1) CK(cudaMemset(h->p2p_buf, 0, p2p_buffer_bytes()));
+    return BNL_OK;
+}
+
 int free_problem(S* h) {
     cudaFree(h->J);
     cudaFree(h->r);
@@ -709,7 +785,7 @@ int free_problem(S* h) {
     cudaFree(h->vecpool);
     cudaFree(h->flagpool);
     cudaFree(h->partial);
-    cudaFree(h->sumsq_partial);
+    cudaFree(h->rpartial);
     cudaFree(h->d_words);
     cudaFree(h->d_idx);
     cudaFree(h->d_count);
@@ -719,9 +795,9 @@ int free_problem(S* h) {
     cudaFree(h->gram_ws);
     cudaFree(h->inc_t);
     cudaFree(h->inc_u);
-    cudaFree(h->inc_partial);
-    cudaFree(h->inc_out2);
-    h->inc_t = h->inc_u = h->inc_partial = h->inc_out2 = nullptr;
+    cudaFree(h->cl_sync);
+    h->inc_t = h->inc_u = nullptr;
+    h->cl_sync = nullptr;
     h->gram_ws = nullptr;
     h->gram_valid = false;
     cudaFree(h->vc.C);
@@ -733,7 +809,7 @@ int free_problem(S* h) {
     cudaFree(h->dc.Lr);
     cudaFree(h->dc.fixidx);
     cudaFree(h->dc.q_dev);
-    h->J = h->r = h->r_trial = h->ydata = h->tvec = h->vecpool = h->partial = h->sumsq_partial = nullptr;
+    h->J = h->r = h->r_trial = h->ydata = h->tvec = h->vecpool = h->partial = h->rpartial = nullptr;
     h->flagpool = nullptr;
     h->d_words = nullptr;
     h->d_idx = nullptr;

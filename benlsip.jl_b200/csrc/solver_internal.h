@@ -15,12 +15,14 @@
 #include <vector>
 
 #include "../../include/benlsip_b200.h"
+#include "cauchy_loop.h"
 #include "common.cuh"
 #include "dense.h"
 #include "gram.h"
 #include "matvec.h"
 #include "models.h"
 #include "p2p.h"
+#include "rowgeom.h"
 #include "vecops.h"
 
 
@@ -81,9 +83,9 @@ struct bnl_solver {
     unsigned char* flagpool = nullptr;
     VecCtx vc{};
     DenseCtx dc{};
-    double* partial = nullptr;
-    double* sumsq_partial = nullptr;
-    int sumsq_blocks = 148 * 8;
+    RowGeom geo{};              // row-chunk geometry of every row reduction (rowgeom.h)
+    double* partial = nullptr;  // [ng][G][T][pstride] partials of the streaming kernels
+    double* rpartial = nullptr; // [ng][G][4] partials of the scalar row reductions
     unsigned long long* d_words = nullptr;
     long long* d_idx = nullptr;
     int* d_count = nullptr;
@@ -95,8 +97,10 @@ struct bnl_solver {
     int hess_mode = 0;          // BNL_HESSIAN_MATRIX_FREE / BNL_HESSIAN_GRAM
     bool gram_valid = false;
     int cauchy_mode = 0;        // BNL_CAUCHY_LITERAL / BNL_CAUCHY_INCREMENTAL
-    double *inc_t = nullptr, *inc_u = nullptr, *inc_partial = nullptr, *inc_out2 = nullptr;
-    int inc_blocks = 148 * 8;
+    double *inc_t = nullptr, *inc_u = nullptr;   // t = J d, u = J s_c (incremental Cauchy search)
+    unsigned int* cl_sync = nullptr;             // arrive counter + broadcast record of the persistent loop kernel
+    double cauchy_guard = 1e-9;                  // relative width of the loop's rounding band
+    bool hv_holds_Hs = false;                    // hv = H*s of the CURRENT s (its slot [ld] = ||J s||^2): vthv(s) is free
 
     // model binding
     int model_id = 0;
@@ -105,6 +109,7 @@ struct bnl_solver {
     double* d_cs = nullptr;
     double* d_xtrue = nullptr;
     std::vector<double> m_x0, m_xlow, m_xupp, m_xtrue;
+    std::vector<double> h_xlow, h_xupp;  // host copy of the bounds in force (log header: count(isfinite, x_l))
     bnl_callback cb_res = nullptr, cb_jac = nullptr, cb_nl = nullptr, cb_jnl = nullptr;
     void* cb_ctx = nullptr;
     bool have_J = false;
@@ -121,12 +126,14 @@ struct bnl_solver {
     // comm
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
-    // peer-memory all-reduce (p2p.h)
-    bool p2p_on = false;
+    bool comm_set = false;      // bnl_comm_init was called (the geometry then follows (nranks, rank))
+    // group mailbox (p2p.h): local at N = 1, mapped into every peer (CUDA IPC) at N > 1
+    bool p2p_on = false;        // N > 1 and all peers mapped: group sums travel as NVLink stores, else by ncclAllGather
     P2PArgs p2p{};
     double* p2p_buf = nullptr;
     unsigned int* p2p_counter = nullptr;
     unsigned long long p2p_epoch = 0;
+    unsigned long long ll_epoch = 0;
     void* p2p_opened[kP2PMaxRanks] = {nullptr};
 
     bnl_stats st{};
@@ -177,6 +184,11 @@ int ensure_pin(S* h, size_t doubles);
 int put_vec(S* h, const double* src, double* dst, size_t count);
 int get_vec(S* h, const double* src_dev, double* dst, size_t count);
 int allreduce(S* h, double* buf, size_t count);
+// finishes a row reduction: partials P[ng][G][T][pstride] -> out[col0..ncols) summed over ALL ranks' rows (fixed tree)
+int row_reduce(S* h, const double* P, int T, long long pstride, int col0, int ncols, double* out);
+int resolve_geometry(S* h);
+int alloc_row_buffers(S* h);
+void p2p_local_setup(S* h);
 int form_gram(S* h);
 int hess_mul(S* h, const double* dv, double* out);
 int vthv_dev(S* h, const double* dv);
@@ -190,7 +202,7 @@ int upload_colmajor(S* h, const double* src, long long rows, int cols, long long
 int eval_jacobian(S* h, const double* dx);
 int gradient(S* h, const double* rbuf, const std::vector<double>& ybar);
 int cauchy_step(S* h, double delta);
-int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool apply_linesearch_and_accumulate);
+int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool apply_linesearch_and_accumulate, bool bounds_given);
 int inner_step(S* h, double delta, double* pred_out);
 int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out);
 int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double omega_tol, double* pix_out, FILE* log);

@@ -82,87 +82,6 @@ __global__ void k_cauchy_eval(VecCtx c, double delta) {
     publish(c.sd, c.sh);
 }
 
-// Incremental form: phi' = u.t + g.d, phi'' = ||t||^2 come from the M-vector kernel (out2 = [tt, ut], all-reduced).
-__global__ void k_cauchy_eval_inc(VecCtx c, double delta, const double* __restrict__ out2) {
-    __shared__ double shd[32];
-    __shared__ long long shl[32];
-    double b = 0.0;
-    double th = INFINITY;
-    long long ind = -1;
-    for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
-        const double di = c.d[i], si = c.s[i];
-        b = fma(c.g[i], di, b);
-        if (!c.fix[i]) {
-            double tt = INFINITY;
-            if (di < 0.0) {
-                const double dl = fmax(c.xlow[i] - c.x[i], -delta);
-                tt = (dl - si) / di;
-            } else if (di > 0.0) {
-                const double du = fmin(c.xupp[i] - c.x[i], delta);
-                tt = (du - si) / di;
-            }
-            if (tt < th) {
-                th = tt;
-                ind = i;
-            }
-        }
-    }
-    b = block_sum(b, shd);
-    block_argmin(th, ind, shd, shl);
-    if (threadIdx.x == 0) {
-        c.sd->phi_p = out2[1] + b;  // dot(s_c,Hd) = (J s_c).(J d)
-        c.sd->phi_pp = out2[0];     // dot(d,Hd)   = ||J d||^2
-        c.sd->theta = th;
-        c.sd->bp_ind = ind;
-        c.sd->bp_dind = (ind >= 0) ? c.d[ind] : 0.0;
-    }
-    publish(c.sd, c.sh);
-}
-
-// Local rows: (first == 0) u += theta*t ; t -= d_ind*J[:,ind] ;  partial2[cta] = {sum t^2, sum u*t}.  theta, ind, d_ind are
-// read from the device scalars of the scan that chose this breakpoint.  first == 1: u = 0, only the sums (t = J d just computed).
-__global__ void __launch_bounds__(256) k_cauchy_inc(VecCtx c, const double* __restrict__ J, long long M, double* __restrict__ t,
-                                                    double* __restrict__ u, double* __restrict__ partial2, int first) {
-    __shared__ double shd[32];
-    const double theta = c.sd->theta, dind = c.sd->bp_dind;
-    const long long ind = c.sd->bp_ind;
-    double tt = 0.0, ut = 0.0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
-        double ti = t[i], ui;
-        if (first) {
-            ui = 0.0;
-        } else {
-            ui = fma(theta, ti, u[i]);
-            ti = fma(-dind, __ldg(J + (size_t)i * c.ld + ind), ti);
-            t[i] = ti;
-        }
-        u[i] = ui;
-        tt = fma(ti, ti, tt);
-        ut = fma(ui, ti, ut);
-    }
-    tt = block_sum(tt, shd);
-    ut = block_sum(ut, shd);
-    if (threadIdx.x == 0) {
-        partial2[2 * blockIdx.x] = tt;
-        partial2[2 * blockIdx.x + 1] = ut;
-    }
-}
-__global__ void k_cauchy_inc_reduce(const double* __restrict__ partial2, int nblocks, double* __restrict__ out2) {
-    __shared__ double shd[32];
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
-        a += partial2[2 * i];
-        b += partial2[2 * i + 1];
-    }
-    a = block_sum(a, shd);
-    b = block_sum(b, shd);
-    if (threadIdx.x == 0) {
-        out2[0] = a;
-        out2[1] = b;
-    }
-}
-
 // :622-635.  breakpoint == 0: s_c += (-phi_p/phi_pp) d.   breakpoint == 1: s_c += theta d; add_active!(ind); d = P(-g)
 template <bool MASK>
 __global__ void k_cauchy_advance(VecCtx c, int breakpoint) {
@@ -225,15 +144,18 @@ __global__ void k_norm_to(VecCtx c, const double* v, int which) {
 }
 
 // minor_iterate :660-665 (trap T1: finite w_l/w_u on the FIXED variables) + projected_cg prologue :702-718
+// bounds_given != 0: projected_cg called with the caller's own w_l / w_u (:690-697) already in c.wl / c.wu
 template <bool MASK>
-__global__ void k_cg_init(VecCtx c, double delta) {
+__global__ void k_cg_init(VecCtx c, double delta, int bounds_given) {
     __shared__ double shd[32];
     double rtv = 0.0, vv = 0.0;
     for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
         const bool f = c.fix[i] != 0;
         const double xm = c.x[i] + c.s[i];  // x_minor :660
-        c.wu[i] = f ? fmin(c.xupp[i] - xm, delta) : INFINITY;
-        c.wl[i] = f ? fmax(c.xlow[i] - xm, -delta) : -INFINITY;
+        if (!bounds_given) {
+            c.wu[i] = f ? fmin(c.xupp[i] - xm, delta) : INFINITY;
+            c.wl[i] = f ? fmax(c.xlow[i] - xm, -delta) : -INFINITY;
+        }
         c.w[i] = 0.0;
         const double ri = c.gm[i];
         c.r[i] = ri;
@@ -552,21 +474,15 @@ __global__ void k_scale_C(VecCtx c) {
     for (size_t i = threadIdx.x; i < tot; i += blockDim.x) c.muC[i] = c.mu * c.C[i];
 }
 
-// dot(rx,rx) :44,:59 -- two-stage fixed-order reduction over M_loc
-__global__ void k_sumsq_stage1(const double* __restrict__ r, long long M, double* __restrict__ partial) {
+// dot(rx,rx) :44,:59 -- one partial per row chunk (rowgeom.h): CTA (gi, b) sums its chunk in a fixed thread pattern
+__global__ void __launch_bounds__(256) k_sumsq_chunks(const double* __restrict__ r, RowGeom geo, double* __restrict__ partial) {
     __shared__ double shd[32];
+    const int gi = blockIdx.x / geo.G, b = blockIdx.x % geo.G;
+    const long long lb = geo.local_begin(gi, b), le = geo.local_end(gi, b);
     double a = 0.0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) a = fma(r[i], r[i], a);
+    for (long long i = lb + threadIdx.x; i < le; i += blockDim.x) a = fma(r[i], r[i], a);
     a = block_sum(a, shd);
     if (threadIdx.x == 0) partial[blockIdx.x] = a;
-}
-__global__ void k_sum_partials(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
-    __shared__ double shd[32];
-    double a = 0.0;
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) a += partial[i];
-    a = block_sum(a, shd);
-    if (threadIdx.x == 0) out[0] = a;
 }
 
 // column-major (Julia) rows x cols, leading dim lds  ->  row-major rows x ldd (zero padded)
@@ -660,16 +576,6 @@ void vk_cauchy_init(const VecCtx& c, bool mask, cudaStream_t st) {
         k_cauchy_init<false><<<1, kVT, 0, st>>>(c);
 }
 void vk_cauchy_eval(const VecCtx& c, double delta, cudaStream_t st) { k_cauchy_eval<<<1, kVT, 0, st>>>(c, delta); }
-void vk_cauchy_inc(const VecCtx& c, const double* J, long long M, double* t, double* u, double* partial2, int nblocks, int first,
-                   cudaStream_t st) {
-    k_cauchy_inc<<<nblocks, 256, 0, st>>>(c, J, M, t, u, partial2, first);
-}
-void vk_cauchy_inc_reduce(const double* partial2, int nblocks, double* out2, cudaStream_t st) {
-    k_cauchy_inc_reduce<<<1, 256, 0, st>>>(partial2, nblocks, out2);
-}
-void vk_cauchy_eval_inc(const VecCtx& c, double delta, const double* out2, cudaStream_t st) {
-    k_cauchy_eval_inc<<<1, kVT, 0, st>>>(c, delta, out2);
-}
 void vk_cauchy_advance(const VecCtx& c, bool mask, int breakpoint, cudaStream_t st) {
     if (mask)
         k_cauchy_advance<true><<<1, kVT, 0, st>>>(c, breakpoint);
@@ -683,11 +589,11 @@ void vk_gminor_nrg(const VecCtx& c, bool mask, cudaStream_t st) {
         k_gminor_nrg<false><<<1, kVT, 0, st>>>(c);
 }
 void vk_norm_to(const VecCtx& c, const double* v, int which, cudaStream_t st) { k_norm_to<<<1, kVT, 0, st>>>(c, v, which); }
-void vk_cg_init(const VecCtx& c, bool mask, double delta, cudaStream_t st) {
+void vk_cg_init(const VecCtx& c, bool mask, double delta, bool bounds_given, cudaStream_t st) {
     if (mask)
-        k_cg_init<true><<<1, kVT, 0, st>>>(c, delta);
+        k_cg_init<true><<<1, kVT, 0, st>>>(c, delta, bounds_given ? 1 : 0);
     else
-        k_cg_init<false><<<1, kVT, 0, st>>>(c, delta);
+        k_cg_init<false><<<1, kVT, 0, st>>>(c, delta, bounds_given ? 1 : 0);
 }
 void vk_cg_step(const VecCtx& c, bool mask, int phase, cudaStream_t st) {
     if (mask)
@@ -717,9 +623,8 @@ void vk_hess_c(const VecCtx& c, const double* v, double* hv, bool add_to_hv, cud
 }
 void vk_add_Ct(const VecCtx& c, const double* pv, double* gout, cudaStream_t st) { k_add_Ct<<<1, kVT, 0, st>>>(c, pv, gout); }
 void vk_scale_C(const VecCtx& c, cudaStream_t st) { k_scale_C<<<1, kVT, 0, st>>>(c); }
-void vk_sumsq(const double* r, long long M, double* partial, int nblocks, double* out, cudaStream_t st) {
-    k_sumsq_stage1<<<nblocks, 256, 0, st>>>(r, M, partial);
-    k_sum_partials<<<1, 256, 0, st>>>(partial, nblocks, out);
+void vk_sumsq_chunks(const double* r, const RowGeom& geo, double* partial, cudaStream_t st) {
+    k_sumsq_chunks<<<geo.ng * geo.G, 256, 0, st>>>(r, geo, partial);
 }
 void vk_transpose_in(const double* src, long long rows, int cols, long long lds, double* dst, int ldd, cudaStream_t st) {
     dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((ldd + 31) / 32));

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "common.cuh"
+#include "rowgeom.h"
 
 namespace bnl {
 
@@ -24,18 +25,10 @@ struct VecCtx {
 void vk_active_reset(const VecCtx& c, const double* xa, const double* sa /*nullable: use xa+sa*/, cudaStream_t st);
 void vk_cauchy_init(const VecCtx& c, bool mask, cudaStream_t st);                 // s = 0; d = P(-g) [mask]
 void vk_cauchy_eval(const VecCtx& c, double delta, cudaStream_t st);              // phi_p, phi_pp, theta, ind
-// Incremental Cauchy search (opt-in, m_lin == 0): t = J d and u = J s_c are kept as M-vectors; a breakpoint is
-//   u += theta*t ; t -= d_ind * J[:,ind]   and   phi'' = ||t||^2, phi' = u.t + g.d   (same algebra as :609-611,:633-635).
-// vk_cauchy_inc updates the local rows and writes per-CTA partials [tt, ut]; vk_cauchy_inc_reduce sums them in fixed
-// order into out2[0..2) (all-reduced by the caller); vk_cauchy_eval_inc is k_cauchy_eval with phi', phi'' from out2.
-void vk_cauchy_inc(const VecCtx& c, const double* J, long long M, double* t, double* u, double* partial2, int nblocks,
-                   int first, cudaStream_t st);
-void vk_cauchy_inc_reduce(const double* partial2, int nblocks, double* out2, cudaStream_t st);
-void vk_cauchy_eval_inc(const VecCtx& c, double delta, const double* out2, cudaStream_t st);
 void vk_cauchy_advance(const VecCtx& c, bool mask, int breakpoint, cudaStream_t st);
 void vk_gminor_nrg(const VecCtx& c, bool mask, cudaStream_t st);                  // gm = hv + g; nrg_g, nrg_gm [mask]
 void vk_norm_to(const VecCtx& c, const double* v, int which, cudaStream_t st);    // which: 0 nrg_g, 1 nrg_gm, 2 pix, 3 norm_g, 4 norm_s
-void vk_cg_init(const VecCtx& c, bool mask, double delta, cudaStream_t st);
+void vk_cg_init(const VecCtx& c, bool mask, double delta, bool bounds_given, cudaStream_t st);  // bounds_given: keep c.wl / c.wu
 void vk_cg_step(const VecCtx& c, bool mask, int phase, cudaStream_t st);          // phase 0: all (mask) / a ; 1: b (general)
 void vk_minor_finish(const VecCtx& c, cudaStream_t st);                           // linesearch + w *= alpha + s += w
 void vk_minor_post(const VecCtx& c, bool mask, double delta, cudaStream_t st);    // gm = hv+g; active_bounds; add_active; nrg
@@ -45,7 +38,8 @@ void vk_pix(const VecCtx& c, bool mask, cudaStream_t st);                       
 void vk_hess_c(const VecCtx& c, const double* v, double* hv, bool add_to_hv, cudaStream_t st);  // cv=C v; Cv_sumsq; hv += C'(muC v)
 void vk_add_Ct(const VecCtx& c, const double* pv, double* gout, cudaStream_t st);  // gout += C' pv
 void vk_scale_C(const VecCtx& c, cudaStream_t st);                                 // muC = mu * C
-void vk_sumsq(const double* r, long long M, double* partial, int nblocks, double* out, cudaStream_t st);
+// per-chunk partials of dot(r,r) (rowgeom.h): partial[ng*G]; the caller finishes with group_reduce / group_sum
+void vk_sumsq_chunks(const double* r, const RowGeom& geo, double* partial, cudaStream_t st);
 void vk_transpose_in(const double* src_colmajor, long long rows, int cols, long long lds, double* dst_rowmajor,
                      int ldd, cudaStream_t st);
 void vk_pack_fix(const unsigned char* fix, int n, unsigned long long* words, cudaStream_t st);

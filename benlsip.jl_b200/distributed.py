@@ -1,17 +1,17 @@
 """Row sharding of the Jacobian across the GPUs of one box: one process per GPU, rows
-[row0, row0 + M_local) per rank, every O(n) quantity replicated, one NCCL all-reduce of n+1 doubles per Hessian
-apply (issued inside the library).  torch.distributed is only the plumbing that carries the ncclUniqueId."""
+[row0, row0 + M_local) per rank, every O(n) quantity replicated, one exchange of the n+1 per-group sums per Hessian
+apply (NVLink peer-memory stores issued inside the library).  torch.distributed is only the plumbing that carries the ncclUniqueId."""
 from __future__ import annotations
 
 import os
 
 
 def shard_rows(M_total: int, nranks: int, rank: int):
-    """Contiguous, balanced row ranges: the first (M_total % nranks) ranks get one extra row."""
-    base, extra = divmod(int(M_total), int(nranks))
-    m_local = base + (1 if rank < extra else 0)
-    row0 = rank * base + min(rank, extra)
-    return row0, m_local
+    """Contiguous row range (row0, M_local) of `rank`: whole groups of the library's fixed row geometry (`bnl_shard_rows`;
+    nranks in {1, 2, 4, 8}), balanced to within a few rows."""
+    from . import shard_rows as _sr
+
+    return _sr(M_total, nranks, rank)
 
 
 def env_rank():

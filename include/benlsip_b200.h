@@ -18,9 +18,11 @@
  *   - one handle = one solver instance bound to one GPU; calls on a handle must be serialised by the
  *     caller (the reference is not re-entrant either: src/basic_tralcnlss.jl:4, lincons mutated in place).
  *   - there is NO CPU fallback: bnl_create fails with BNL_ENODEV when no sm_100 device is visible.
- *   - multi-GPU: one process (one handle) per GPU; rows of J / r are sharded, every O(n) quantity is
- *     replicated; the only collective is an all-reduce of n+1 doubles per Hessian apply (fused NVLink
- *     peer-memory kernels, NCCL as the fallback and for the n^2 Gram).
+ *   - multi-GPU: one process (one handle) per GPU; rows of J / r are sharded (bnl_shard_rows), every O(n)
+ *     quantity is replicated; the only collective is the exchange of the n+1 per-group sums of a Hessian
+ *     apply (NVLink stores into peer-mapped mailboxes fused into the reduction kernel; ncclAllGather as the
+ *     fallback; ncclAllReduce only for the n^2 Gram of the opt-in Gram mode).  Results are bit-identical for
+ *     1, 2, 4 and 8 GPUs.
  */
 #ifndef BENLSIP_B200_H
 #define BENLSIP_B200_H
@@ -83,7 +85,9 @@ typedef struct bnl_stats {
     int64_t gram_count;   /* Gram formations (BNL_HESSIAN_GRAM)                                        */
     double gram_ms;
     int64_t p2p_allreduces; /* all-reduces done by the fused NVLink peer-memory kernels instead of NCCL       */
-    int64_t inc_breakpoints; /* breakpoints handled by the incremental Cauchy update (no J pass)                */
+    int64_t inc_breakpoints; /* breakpoints handled by the device-side incremental Cauchy loop (no J pass)          */
+    int64_t cauchy_loop_launches; /* launches of the persistent breakpoint-loop kernel                               */
+    int64_t cauchy_literal_evals; /* literal Hd = H*d evaluations the guarded loop asked for (:633-635)              */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */
@@ -97,10 +101,13 @@ typedef struct bnl_inner_record {
  * same mathematics, different rounding (kappa(G) = kappa(J)^2) => opt-in, validated separately.        */
 enum { BNL_HESSIAN_MATRIX_FREE = 0, BNL_HESSIAN_GRAM = 1 };
 
-/* How cauchy_step (src/basic_tralcnlss.jl:574-639) obtains phi' and phi'' after a breakpoint.  LITERAL (default): a fresh
- * Hd = H*d per breakpoint (:633), one pass over J each.  INCREMENTAL (opt-in, bound-only problems): d only loses one
- * component per breakpoint, so t = J d and u = J s_c are updated in place (one strided column of J + two M-vector
- * streams) and phi'' = ||t||^2, phi' = u.t + g.d -- same algebra and decisions, different rounding.                     */
+/* How cauchy_step (src/basic_tralcnlss.jl:574-639) obtains phi' and phi'' after a breakpoint.  LITERAL: a fresh Hd = H*d
+ * per breakpoint (:633), one pass over J each.  INCREMENTAL (default; used when the projection is the bound mask, i.e.
+ * m_lin == 0, with at most 8 nonlinear constraints, in matrix-free mode): d only loses one component per breakpoint, so
+ * t = J d and u = J s_c are updated in place (one strided column of J + two M-vector streams) by ONE persistent device
+ * kernel that walks the breakpoints without host round trips.  The loop is guarded: a decision inside a rounding band, and
+ * every interior minimiser (whose step length enters the iterate), is re-evaluated with the literal Hd = H*d, so the Cauchy
+ * point is bit-identical to the literal search's.  Environment: BNL_CAUCHY=literal selects LITERAL at bnl_create.           */
 enum { BNL_CAUCHY_LITERAL = 0, BNL_CAUCHY_INCREMENTAL = 1 };
 
 /* Built-in device-side models (definitions in oracle/models.py, the executable spec). */
@@ -130,6 +137,10 @@ int bnl_comm_init(bnl_handle h, int nranks, int rank, const void* id128);
 /* p2p_allreduce = 1 when the n+1-double all-reduce runs as fused NVLink peer-memory kernels (CUDA IPC mailboxes;
  * default when all ranks could map each other; BNL_P2P_ALLREDUCE=0 forces NCCL). */
 int bnl_comm_info(bnl_handle h, int32_t* nranks, int32_t* rank, int32_t* p2p_allreduce);
+/* The rows rank `rank` of `nranks` (1, 2, 4 or 8) must own: every sum over residual rows is taken over a fixed geometry of
+ * 8 groups x G chunks that depends only on M_total, so results are bit-identical for any supported GPU count; a rank owns
+ * whole groups.  Pure host function (no device needed).                                                                 */
+int bnl_shard_rows(int64_t M_total, int32_t nranks, int32_t rank, int64_t* row0, int64_t* M_local);
 
 /* ---- problem: MixedConstraints(A, chol_aat; l, u), src/polyhedral_constraints.jl:9-18, and
  *      chol_aat = cholesky(A*A'), src/basic_tralcnlss.jl:206.  M_local rows [row0,row0+M_local) of
@@ -181,6 +192,11 @@ int bnl_cauchy_step(bnl_handle h, const double* x, const double* g, double delta
 /* projected_cg(g_minor,H,w_l,w_u,lincons,kappa2) :690-764 (w_l/w_u built as in minor_iterate :662-665) */
 int bnl_projected_cg(bnl_handle h, const double* x, const double* s, const double* g_minor, double delta,
                      double* w, int32_t* cg_status, int32_t* iters);
+/* projected_cg(g_minor,H,w_l,w_u,lincons,kappa2) :690-764 with the caller's own w_l / w_u and the current fixvars */
+int bnl_projected_cg_bounds(bnl_handle h, const double* g_minor, const double* w_l, const double* w_u, double* w,
+                            int32_t* cg_status, int32_t* iters);
+/* linesearch(g_model,H,w,w_l,w_u,lincons.fixvars) :766-791 -> alpha */
+int bnl_linesearch(bnl_handle h, const double* g_model, const double* w, const double* w_l, const double* w_u, double* alpha);
 /* inner_step(x,g,H,chol_aat,lincons,delta,nb_minor_step,kappa2,kappa3) :394-460 -> (s, model_reduction) */
 int bnl_inner_step(bnl_handle h, const double* x, const double* g, double delta, double* s, double* pred);
 /* new_point(x,y,mu,...) :32-49 -> mx, g (J, C kept in the handle as H) */

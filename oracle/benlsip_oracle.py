@@ -514,9 +514,13 @@ def inner_step(x, g, H: AlHessian, chol_aat_L, lincons: MixedConstraints, delta,
 # --------------------------------------------------------------------------------------
 # Logging in the reference's benlsip.out format  (src/misc.jl:1-80)
 # --------------------------------------------------------------------------------------
-def _c_exp(fmt_prec: int, v: float) -> str:
-    """C/Julia @sprintf("%.{p}e")."""
-    return f"%.{fmt_prec}e" % v
+def _jl_e(prec: int, v: float) -> str:
+    """Julia @sprintf("%.{p}e"): C formatting for finite values, `NaN` / `Inf` / `-Inf` otherwise (Julia's Printf)."""
+    if math.isnan(v):
+        return "NaN"
+    if math.isinf(v):
+        return "Inf" if v > 0 else "-Inf"
+    return f"%.{prec}e" % v
 
 
 def print_tralcnllss_header(n, d, p, m, x_l, x_u, crit_tol, feas_tol, tau, eta1, eta2, gamma1, gamma2, io):
@@ -555,16 +559,16 @@ def print_outer_iter_header(k, objective, nl_feas, mu, pix, omega, io, first=Fal
     w("                          Outer iter %d\n" % k)
     w("  objective    nl feasibility     μ      criticality   tolerance\n")
     if first:
-        w("%.7e   %.6e  %.2e        -         %.2e" % (objective, nl_feas, mu, omega))
+        w("%s   %s  %s        -         %s" % (_jl_e(7, objective), _jl_e(6, nl_feas), _jl_e(2, mu), _jl_e(2, omega)))
     else:
-        w("%.7e   %.6e  %.2e     %.2e     %.2e" % (objective, nl_feas, mu, pix, omega))
+        w("%s   %s  %s     %s     %s" % (_jl_e(7, objective), _jl_e(6, nl_feas), _jl_e(2, mu), _jl_e(2, pix), _jl_e(2, omega)))
     w("\n" + "=" * 80 + "\n")
     w("iter     AL value       ||s||        Δ          ρ\n")
 
 
 def print_inner_iter(k, obj, norm_step, radius, rho, io):
     """src/misc.jl:70-80."""
-    io.write("%4d   %.6e   %.2e   %.2e   %.2e\n" % (k, obj, norm_step, radius, rho))
+    io.write("%4d   %s   %s   %s   %s\n" % (k, _jl_e(6, obj), _jl_e(2, norm_step), _jl_e(2, radius), _jl_e(2, rho)))
 
 
 # --------------------------------------------------------------------------------------

@@ -42,13 +42,21 @@ def test_no_cpu_fallback():
 
 
 def test_shard_rows_partition():
-    for M, N in [(10, 1), (10, 3), (10_000_000, 8), (7, 8), (0, 2)]:
+    """bnl_shard_rows: whole groups of the fixed 8 x G chunk geometry (csrc/rowgeom.h) -- contiguous, disjoint, covering,
+    balanced; the same chunk boundaries whatever the rank count, which is what makes the row reductions N-invariant."""
+    for M, N in [(10, 1), (10, 2), (10_000_000, 8), (10_000_000, 4), (7, 8), (0, 2), (200_003, 8), (1001, 2)]:
         spans = [shard_rows(M, N, r) for r in range(N)]
         assert spans[0][0] == 0
         assert sum(m for _, m in spans) == M
         for (a0, am), (b0, _) in zip(spans, spans[1:]):
             assert a0 + am == b0
-        assert max(m for _, m in spans) - min(m for _, m in spans) <= 1
+        assert max(m for _, m in spans) - min(m for _, m in spans) <= max(8 // N, 1) * 148
+    # group boundaries do not move with the rank count
+    b8 = [shard_rows(10_000_000, 8, r)[0] for r in range(8)]
+    assert [shard_rows(10_000_000, 4, r)[0] for r in range(4)] == b8[::2]
+    assert [shard_rows(10_000_000, 2, r)[0] for r in range(2)] == b8[::4]
+    with pytest.raises(ValueError):
+        shard_rows(10, 3, 0)  # the geometry has 8 groups: 1, 2, 4 or 8 ranks
 
 
 def test_status_strings():

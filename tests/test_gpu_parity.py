@@ -36,23 +36,23 @@ def assert_matches_golden(name, tr_g, x_g, tol=1e-10):
         assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"] and abs(a["mx"] - b["mx"]) <= 1e-10 * abs(b["mx"])
 
 
-def assert_parity_with_live_oracle(tr_g, x_g, tr_o, x_o, tol=1e-10):
-    """Against the oracle run on THIS host.  NumPy/OpenBLAS sums in a host-dependent order (kernel, thread count), so the
-    oracle's own late iterations can flicker from box to box: equal counts => tight comparison,
-    otherwise the documented floor (outer count within 1, the first 8 inner iterations identical, iterate to 1e-6)."""
+def assert_parity_with_live_oracle(name, tr_g, x_g, tr_o, x_o, tol=1e-10):
+    """Against the oracle run on THIS host.  The exact assertions are the golden ones (assert_matches_golden, always
+    enforced).  NumPy/OpenBLAS sums in a host-dependent order (kernel, thread count), so the ORACLE's own late iterations
+    can deviate from its committed golden on some hosts: that case is reported as an explicit xfail of the live comparison
+    (it says nothing about the CUDA path, which has already matched the golden); otherwise the comparison is tight."""
+    g = _golden(name)
+    oracle_counts = (tr_o["outer_iters"], tr_o["inner_iters"], tr_o.get("cg_iters", 0), tr_o.get("breakpoints", 0))
+    golden_counts = (g["outer_iters"], g["inner_iters"], g["cg_iters"], g["breakpoints"])
+    if oracle_counts != golden_counts:
+        pytest.xfail(f"live oracle on this host deviates from its own committed golden {name}: {oracle_counts} vs {golden_counts} "
+                     "(host BLAS summation order); the CUDA path matched the golden exactly")
     st = tr_g["stats"]
-    same = (tr_g["outer_iters"], st["inner_iters"], st["cg_iters"], st["breakpoints"]) == \
-           (tr_o["outer_iters"], tr_o["inner_iters"], tr_o.get("cg_iters", 0), tr_o.get("breakpoints", 0))
-    if same:
-        assert rel(x_g, x_o) < tol
-        assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
-        for a, b in zip(tr_g["inner"], tr_o["inner"]):
-            assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"] and abs(a["mx"] - b["mx"]) <= 1e-10 * abs(b["mx"])
-    else:
-        assert abs(tr_g["outer_iters"] - tr_o["outer_iters"]) <= 1
-        for a, b in list(zip(tr_g["inner"], tr_o["inner"]))[:8]:
-            assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"] and abs(a["mx"] - b["mx"]) <= 1e-9 * abs(b["mx"])
-        assert rel(x_g, x_o) < 1e-6
+    assert (tr_g["outer_iters"], st["inner_iters"], st["cg_iters"], st["breakpoints"]) == oracle_counts
+    assert rel(x_g, x_o) < tol
+    assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+    for a, b in zip(tr_g["inner"], tr_o["inner"]):
+        assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"] and abs(a["mx"] - b["mx"]) <= 1e-10 * abs(b["mx"])
 
 
 @pytest.fixture()
@@ -122,16 +122,16 @@ def test_gram_dmma_matches_numpy(S):
 # ---------------------------------------------------------------------------------------------------------
 # K11: device models against oracle/models.py
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind,M,n,row0", [("glm", 4096, 64, 0), ("glm", 3001, 250, 0), ("glm", 1500, 1024, 70000),
-                                           ("expsum", 4096, 16, 0), ("expsum", 5000, 64, 123)])
-def test_builtin_models_match_oracle(S, kind, M, n, row0):
+@pytest.mark.parametrize("kind,Mtot,n,nranks,rank", [("glm", 4096, 64, 1, 0), ("glm", 3001, 250, 1, 0), ("glm", 71500, 1024, 8, 7),
+                                                     ("glm", 9000, 96, 2, 1), ("expsum", 4096, 16, 1, 0), ("expsum", 5140, 64, 4, 2)])
+def test_builtin_models_match_oracle(S, kind, Mtot, n, nranks, rank):
+    """Rows [row0, row0 + M) of a global problem: the shard of `rank` of `nranks` (bnl_shard_rows)."""
+    row0, M = B.shard_rows(Mtot, nranks, rank)
     if kind == "glm":
         P = GlmProblem(M, n, seed=3, row0=row0)
         mid = B.MODEL_GLM
         seed = 3
-        Mtot = M + row0
     else:
-        Mtot = M + row0 + 17
         P = ExpSumProblem(M, n, seed=1, row0=row0, M_total=Mtot)
         mid = B.MODEL_EXPSUM
         seed = 1
@@ -317,9 +317,21 @@ def test_glm_full_solve_parity(S, M, n):
     P = GlmProblem(M, n, seed=3)
     x_o, tr_o, x_g, tr_g = _solve_both(S, P, B.MODEL_GLM, 3)
     assert_matches_golden(f"glm_{M}_{n}", tr_g, x_g)
-    assert_parity_with_live_oracle(tr_g, x_g, tr_o, x_o)
-    obj_g, obj_o = S.residuals(x_g, False)[1], float(np.sum(P.residuals(x_o) ** 2))
-    assert abs(obj_g - obj_o) <= 1e-9 * obj_o
+    obj_g, obj_o = S.residuals(x_g, False)[1], float(np.sum(P.residuals(np.array(_golden(f"glm_{M}_{n}")["x"])) ** 2))
+    assert abs(obj_g - obj_o) <= 1e-10 * obj_o
+    # the literal search (a Hessian apply per breakpoint, :633) gives the SAME iterate bit for bit: the default device-side
+    # breakpoint loop only ever lets literal numbers reach the iterate
+    st_inc = tr_g["stats"]
+    assert st_inc["inc_breakpoints"] == st_inc["breakpoints"] and st_inc["cauchy_loop_launches"] >= st_inc["inner_iters"]
+    S.set_cauchy_mode(B.CAUCHY_LITERAL)
+    tr_l = {}
+    x_l, _ = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr_l)
+    S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+    assert np.array_equal(x_l, x_g) and np.array_equal(tr_l["fixvars_words"], tr_g["fixvars_words"])
+    assert tr_l["stats"]["inc_breakpoints"] == 0 and tr_l["stats"]["breakpoints"] == st_inc["breakpoints"]
+    assert tr_l["stats"]["j_passes"] > st_inc["j_passes"]
+    assert_matches_golden(f"glm_{M}_{n}", tr_l, x_l)
+    assert_parity_with_live_oracle(f"glm_{M}_{n}", tr_g, x_g, tr_o, x_o)
 
 
 def _assert_trace_prefix(tr_g, tr_o, nprefix, mx_rtol=1e-12, pix_rtol=1e-5):
@@ -386,9 +398,9 @@ def test_cfg4_family_mixed_constraints_full_solve_parity():
     assert tr_g["mu"] == _golden("mixed_600_24_4")["mu"] and tr_g["mu"] > 10.0
     assert_matches_golden("mixed_600_24_4", tr_g, x_g)
     assert rel(y_g, np.array(_golden("mixed_600_24_4")["y"])) < 1e-8
-    assert_parity_with_live_oracle(tr_g, x_g, tr_o, x_o)
     assert abs(P.nlconstraints(x_g)[0]) < 1e-8 and np.max(np.abs(P.A @ x_g - P.b)) < 1e-12
     assert st["chol_rebuilds"] > 0
+    assert_parity_with_live_oracle("mixed_600_24_4", tr_g, x_g, tr_o, x_o)
 
 
 def test_cfg4_family_on_device_matches_oracle(S):
@@ -411,7 +423,7 @@ def test_cfg4_family_on_device_matches_oracle(S):
     x_g, y_g = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr_g, **kw)
     assert_matches_golden("mixed_600_24_4", tr_g, x_g)
     assert tr_g["mu"] == _golden("mixed_600_24_4")["mu"] and rel(y_g, np.array(_golden("mixed_600_24_4")["y"])) < 1e-8
-    assert_parity_with_live_oracle(tr_g, x_g, tr_o, x_o)
+    assert_parity_with_live_oracle("mixed_600_24_4", tr_g, x_g, tr_o, x_o)
 
 
 def test_cfg5_family_ill_conditioned_inner_steps(S):
@@ -463,41 +475,84 @@ def test_gram_mode_solve_matches_matrix_free_and_oracle(S, M, n):
     assert rel(hv_g, hv_f) < 1e-12 and abs(q_g - q_f) <= 1e-12 * q_f
 
 
-@pytest.mark.parametrize("M,n", [(4096, 64), (20000, 256), (6000, 1024)])
-def test_incremental_cauchy_mode_matches_oracle(S, M, n):
-    """Opt-in incremental Cauchy search (t = J d, u = J s_c updated per breakpoint instead of a Hessian apply each):
-    same decisions as the literal search => same iteration / breakpoint counts and final iterate as the oracle."""
-    P = GlmProblem(M, n, seed=3)
-    tr_o, tr_g = {}, {}
-    x_o, _ = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp, trace=tr_o)
-    S.set_problem(P.M, P.n)
-    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
-    S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
-    x_g, _ = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr_g)
-    st = tr_g["stats"]
-    assert st["inc_breakpoints"] == st["breakpoints"]
-    assert st["j_passes"] < tr_o["counters"]["hess_mul"] + tr_o["counters"]["vthv"] + tr_o["counters"]["jtw"]
-    if (M, n) == (4096, 64):
-        # this case ends exactly on the pix <= crit_tol threshold: any re-rounding (this mode, Gram mode) adds one last outer
-        # iteration (measured 8 vs 7); the iterate still agrees to 5e-9
-        assert tr_g["outer_iters"] - tr_o["outer_iters"] in (0, 1) and rel(x_g, x_o) < 5e-9
-    else:
-        assert_matches_golden(f"glm_{M}_{n}", tr_g, x_g)
-        assert_parity_with_live_oracle(tr_g, x_g, tr_o, x_o)
-    S.set_cauchy_mode(B.CAUCHY_LITERAL)
-
-
-def test_incremental_cauchy_step_equals_literal(S):
+def test_device_cauchy_loop_equals_literal_search(S):
+    """cauchy_step / inner_step through the default device-side breakpoint loop vs the literal search (:574-639): the Cauchy
+    point, the step, the predicted reduction and the active set are bit-identical; only the pass count differs."""
     P, x, g, H, L0, cons = _glm_state(S, 3000, 96)
     for delta in (1e-3, 0.05, 10.0):
         S.set_cauchy_mode(B.CAUCHY_LITERAL)
+        S.reset_stats()
         s_lit, pred_lit = S.inner_step(x, g, delta)
-        w_lit = S.fixvars_words()
+        w_lit, st_lit = S.fixvars_words(), S.stats()
         S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+        S.reset_stats()
         s_inc, pred_inc = S.inner_step(x, g, delta)
-        assert rel(s_inc, s_lit) < 1e-12 and abs(pred_inc - pred_lit) <= 1e-12 * abs(pred_lit)
+        st_inc = S.stats()
+        assert np.array_equal(s_inc, s_lit) and pred_inc == pred_lit
         assert np.array_equal(S.fixvars_words(), w_lit)
+        assert st_inc["breakpoints"] == st_lit["breakpoints"] == st_inc["inc_breakpoints"]
+        assert st_inc["cauchy_loop_launches"] >= 1 and st_inc["j_passes"] <= st_lit["j_passes"]
+
+
+def test_device_cauchy_loop_guard_band_forces_literal_evaluations(S):
+    """With an absurdly wide rounding band every decision is 'inside the band': the loop must hand EVERY breakpoint to the
+    literal evaluation and still produce the literal result (the guard path is the one that protects parity)."""
+    import os
+    P, x, g, H, L0, cons = _glm_state(S, 3000, 96)
     S.set_cauchy_mode(B.CAUCHY_LITERAL)
+    s_lit, pred_lit = S.inner_step(x, g, 0.05)
+    w_lit = S.fixvars_words()
+    os.environ["BNL_CAUCHY_GUARD"] = "1e30"
+    try:
+        S2 = B.Solver(0)
+    finally:
+        del os.environ["BNL_CAUCHY_GUARD"]
+    S2.set_problem(3000, 96)
+    S2.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+    S2.eval_jacobian(x)
+    S2.reset_stats()
+    s2, pred2 = S2.inner_step(x, g, 0.05)
+    st = S2.stats()
+    assert np.array_equal(s2, s_lit) and pred2 == pred_lit and np.array_equal(S2.fixvars_words(), w_lit)
+    assert st["cauchy_literal_evals"] >= st["breakpoints"] >= 1
+    S2.close()
+    S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+
+
+def test_device_cauchy_loop_with_nonlinear_constraint_block(S):
+    """Bounds + one nonlinear (sphere) constraint, no linear equalities: the loop carries the mu C'C part of AlHessian
+    (:92-106) itself; result bit-identical to the literal search, which applies H = J'J + mu C'C per breakpoint."""
+    M, n = 2000, 48
+    P = GlmProblem(M, n, seed=3)
+    S.set_problem(M, n, None, P.xlow, P.xupp, p=1)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+    S.use_builtin_nlcons(B.NLCONS_SPHERE, 3.0)
+    x = P.x0.copy()
+    x[::5] = 0.4
+    y = np.array([0.3])
+    for mu in (10.0, 1e4):
+        res = []
+        for mode in (B.CAUCHY_LITERAL, B.CAUCHY_INCREMENTAL):
+            S.set_cauchy_mode(mode)
+            mx, g, cx = S.new_point(x, y, mu)
+            S.reset_stats()
+            s, pred = S.inner_step(x, g, 0.3)
+            res.append((s, pred, S.fixvars_words(), S.stats()))
+        assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1] and np.array_equal(res[0][2], res[1][2])
+        assert res[1][3]["inc_breakpoints"] == res[1][3]["breakpoints"] == res[0][3]["breakpoints"]
+        # and against the oracle with the same H
+        J, r = P.jac_res(x), P.residuals(x)
+        Cm = (2.0 * x)[None, :]
+        c = np.array([x @ x - 3.0])
+        g_ref = J.T @ r + Cm.T @ (y + mu * c)
+        assert rel(g, g_ref) < 1e-12
+        H = O.AlHessian(J, Cm, mu)
+        L0 = O._cholesky_lower(np.zeros((0, 0)))
+        cons = O.MixedConstraints(np.zeros((0, n)), L0, l=P.xlow, u=P.xupp)
+        s_ref, pred_ref = O.inner_step(x, g_ref, H, L0, cons, 0.3, 50, 0.1, 0.1)
+        assert rel(res[1][0], s_ref) < 1e-9 and abs(res[1][1] - pred_ref) <= 1e-9 * abs(pred_ref)
+        assert np.array_equal(res[1][2], cons.fixvars_words())
+    S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
 
 
 def test_native_outer_loop_equals_host_outer_loop(S, tmp_path):
