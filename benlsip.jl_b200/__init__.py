@@ -71,7 +71,7 @@ class Stats(C.Structure):
                [(k, C.c_double) for k in ("hess_mul_ms", "vthv_ms", "jtw_ms", "res_eval_ms", "jac_eval_ms", "solve_ms")] + \
                [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double),
                 ("p2p_allreduces", C.c_int64), ("inc_breakpoints", C.c_int64), ("cauchy_loop_launches", C.c_int64),
-                ("cauchy_literal_evals", C.c_int64)]
+                ("cauchy_literal_evals", C.c_int64), ("t0_reuses", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -79,7 +79,8 @@ class Stats(C.Structure):
 
 class InnerRecord(C.Structure):
     _fields_ = [("k", C.c_int32), ("nb_fix", C.c_int32), ("mx", C.c_double), ("norm_s", C.c_double), ("delta", C.c_double),
-                ("rho", C.c_double), ("pix", C.c_double), ("pred", C.c_double)]
+                ("rho", C.c_double), ("pix", C.c_double), ("pred", C.c_double), ("omega_tol", C.c_double),
+                ("breakpoints_cum", C.c_int64), ("cg_cum", C.c_int64)]
 
 
 CALLBACK = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
@@ -520,7 +521,8 @@ class Solver:
         self._ck(self.lib.bnl_get_inner_log(self.h, None, 0, C.byref(cnt)))
         arr = (InnerRecord * max(cnt.value, 1))()
         self._ck(self.lib.bnl_get_inner_log(self.h, arr, cnt.value, C.byref(cnt)))
-        return [dict(k=a.k, nb_fix=a.nb_fix, mx=a.mx, norm_s=a.norm_s, delta=a.delta, rho=a.rho, pix=a.pix, pred=a.pred)
+        return [dict(k=a.k, nb_fix=a.nb_fix, mx=a.mx, norm_s=a.norm_s, delta=a.delta, rho=a.rho, pix=a.pix, pred=a.pred,
+                     omega_tol=a.omega_tol, bp_cum=a.breakpoints_cum, cg_cum=a.cg_cum)
                 for a in arr[: cnt.value]]
 
     def time_kernel(self, kind, reps=10):

@@ -142,6 +142,7 @@ int bnl_set_params(bnl_handle h, const bnl_params* p) {
     if (!((0 < p->eta1) && (p->eta1 <= p->eta2) && (p->eta2 < 1) && (0 < p->gamma1) && (p->gamma1 < 1) && (1 < p->gamma2)))
         return h->fail(BNL_EASSERT, "AssertionError: Invalid trust region updates paramaters");
     h->prm = *p;
+    h->t0_valid = false;
     sync_params_to_ctx(h);
     return BNL_OK;
 }
@@ -498,6 +499,7 @@ int bnl_upload_jacobian(bnl_handle h, const double* J_colmajor, int64_t ldj) {
     RET(upload_colmajor(h, J_colmajor, h->M, h->n, ldj, h->J, h->ld));
     h->have_J = true;
     h->gram_valid = false;
+    h->t0_valid = false;
     return BNL_OK;
 }
 
@@ -870,6 +872,7 @@ int bnl_linesearch(bnl_handle h, const double* g_model, const double* w, const d
 
 int bnl_inner_step(bnl_handle h, const double* x, const double* g, double delta, double* s, double* pred) {
     ENTER();
+    h->t0_valid = false;
     RET(put_vec(h, x, h->vc.x, h->n));
     RET(put_vec(h, g, h->vc.g, h->n));
     double pr = 0.0;
@@ -895,6 +898,7 @@ int bnl_new_point(bnl_handle h, const double* x, const double* y, double mu, dou
 static int solve_subproblem_host(bnl_handle h, const double* x0, const double* y, double mu, double omega_tol, double* x,
                                  double* cx, double* pix, FILE* log) {
     if (!x0) return BNL_EINVAL;
+    h->t0_valid = false;
     cudaEvent_t e0 = h->ev_t0, e1 = h->ev_t1;
     RET(put_vec(h, x0, h->vc.x, h->n));
     CK(cudaEventRecord(e0, h->stream));

@@ -365,6 +365,7 @@ int eval_jacobian(S* h, const double* dx) {
     }
     h->have_J = true;
     h->gram_valid = false;
+    h->t0_valid = false;
     h->st.jac_eval++;
     if (h->hess_mode == BNL_HESSIAN_GRAM) RET(form_gram(h));
     return BNL_OK;
@@ -372,6 +373,7 @@ int eval_jacobian(S* h, const double* dx) {
 
 // g = Jx'*rx + Cx'*y_bar  (:45, :74)
 int gradient(S* h, const double* rbuf, const std::vector<double>& ybar) {
+    h->t0_valid = false;
     RET(jtw_dev(h, rbuf, h->vc.hv));
     CK(cudaMemcpyAsync(h->vc.g, h->vc.hv, (size_t)h->ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (h->p > 0) {
@@ -402,17 +404,27 @@ int cauchy_step_incremental(S* h, double delta) {
         const size_t mb = std::max<size_t>(h->M, 16) * sizeof(double);
         CK(cudaMalloc(&h->inc_t, mb));
         CK(cudaMalloc(&h->inc_u, mb));
+        CK(cudaMalloc(&h->inc_t0, mb));
         CK(cudaMalloc(&h->cl_sync, cauchy_loop_sync_bytes()));
+        h->t0_valid = false;
     }
     vk_active_reset(c, c.x, nullptr, h->stream);  // :591
     vk_cauchy_init(c, true, h->stream);           // s_c = 0 ; d = P(-g) :592
     h->st.kernel_launches += 2;
-    {   // t = J d  (one J pass; the loop computes ||t||^2 itself, in the chunk geometry)
-        EvScope ev(h, 1);
-        CK(mv_launch(MODE_JV, h->plan, h->geo, h->J, c.d, nullptr, h->inc_t, h->partial, h->stream));
+    if (h->t0_valid) {
+        // a rejected step left x, g and J untouched (:358-366): d = P(-g) is the same vector bit for bit, so is t = J d
+        CK(cudaMemcpyAsync(h->inc_t, h->inc_t0, (size_t)h->M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        h->st.t0_reuses++;
+    } else {
+        {   // t = J d  (one J pass; the loop computes ||t||^2 itself, in the chunk geometry)
+            EvScope ev(h, 1);
+            CK(mv_launch(MODE_JV, h->plan, h->geo, h->J, c.d, nullptr, h->inc_t, h->partial, h->stream));
+        }
+        KLAUNCH();
+        h->st.j_passes += 1;
+        CK(cudaMemcpyAsync(h->inc_t0, h->inc_t, (size_t)h->M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        h->t0_valid = true;
     }
-    KLAUNCH();
-    h->st.j_passes += 1;
     h->st.jv++;
     CauchyLoopArgs a{};
     a.c = c;
@@ -719,6 +731,9 @@ int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double o
         pix = h->sh->pix;
         rec.pix = pix;
         rec.nb_fix = h->sh->nb_fix;
+        rec.omega_tol = omega_tol;
+        rec.breakpoints_cum = h->st.breakpoints;
+        rec.cg_cum = h->st.cg_iters;
         if (h->ilog.size() < (1u << 20)) h->ilog.push_back(rec);
         solved = pix < omega_tol;  // :373
         ++k;
@@ -796,7 +811,9 @@ int free_problem(S* h) {
     cudaFree(h->inc_t);
     cudaFree(h->inc_u);
     cudaFree(h->cl_sync);
-    h->inc_t = h->inc_u = nullptr;
+    cudaFree(h->inc_t0);
+    h->inc_t = h->inc_u = h->inc_t0 = nullptr;
+    h->t0_valid = false;
     h->cl_sync = nullptr;
     h->gram_ws = nullptr;
     h->gram_valid = false;

@@ -98,6 +98,8 @@ struct bnl_solver {
     bool gram_valid = false;
     int cauchy_mode = 0;        // BNL_CAUCHY_LITERAL / BNL_CAUCHY_INCREMENTAL
     double *inc_t = nullptr, *inc_u = nullptr;   // t = J d, u = J s_c (incremental Cauchy search)
+    double* inc_t0 = nullptr;                    // J P(-g) of the current (x, g, J): reused by the searches after rejected steps
+    bool t0_valid = false;
     unsigned int* cl_sync = nullptr;             // arrive counter + broadcast record of the persistent loop kernel
     double cauchy_guard = 1e-9;                  // relative width of the loop's rounding band
     bool hv_holds_Hs = false;                    // hv = H*s of the CURRENT s (its slot [ld] = ||J s||^2): vthv(s) is free

@@ -88,12 +88,15 @@ typedef struct bnl_stats {
     int64_t inc_breakpoints; /* breakpoints handled by the device-side incremental Cauchy loop (no J pass)          */
     int64_t cauchy_loop_launches; /* launches of the persistent breakpoint-loop kernel                               */
     int64_t cauchy_literal_evals; /* literal Hd = H*d evaluations the guarded loop asked for (:633-635)              */
+    int64_t t0_reuses;            /* Cauchy searches after a rejected step that reused t = J P(-g) instead of a J pass */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */
 typedef struct bnl_inner_record {
     int32_t k, nb_fix;
     double mx, norm_s, delta, rho, pix, pred;
+    double omega_tol;                  /* the subproblem tolerance pix is tested against (:373) */
+    int64_t breakpoints_cum, cg_cum;   /* Cauchy breakpoints / projected-CG iterations since bnl_reset_stats */
 } bnl_inner_record;
 
 /* How Base.:*(H,v) / vthv are evaluated.  MATRIX_FREE (default) is the reference's J'(Jv) (src/basic_tralcnlss.jl:102-106),

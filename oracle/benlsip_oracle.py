@@ -606,6 +606,9 @@ def solve_subproblem(x0, y, mu, residuals, nlconstraints, jac_res, jac_nlcons, c
         if trace is not None:
             trace["inner"][-1]["pix"] = pix
             trace["inner"][-1]["nb_fix"] = lincons.nb_fix()
+            trace["inner"][-1]["omega_tol"] = omega_tol
+            trace["inner"][-1]["bp_cum"] = trace.get("breakpoints", 0)
+            trace["inner"][-1]["cg_cum"] = trace.get("cg_iters", 0)
         solved = pix < omega_tol
         k += 1
     if trace is not None:

@@ -18,7 +18,9 @@ def run(P, **kw):
     return dict(x=x.tolist(), y=np.asarray(y).tolist(), outer_iters=tr["outer_iters"], inner_iters=tr["inner_iters"],
                 minor_iters=tr.get("minor_iters", 0), cg_iters=tr.get("cg_iters", 0), breakpoints=tr.get("breakpoints", 0),
                 mu=tr["mu"], fixvars_words=[int(w) for w in tr["fixvars_words"]],
-                inner=[dict(k=r["k"], mx=r["mx"], delta=r["delta"], pix=r["pix"], nb_fix=r["nb_fix"]) for r in tr["inner"][:40]])
+                objective=float(np.sum(P.residuals(x) ** 2)),
+                inner=[{k: r[k] for k in ("k", "mx", "delta", "pix", "nb_fix", "rho", "pred", "norm_s", "omega_tol", "bp_cum", "cg_cum")}
+                       for r in tr["inner"]])
 
 
 cases = {

@@ -24,7 +24,7 @@ out = dict(M=M, n=n, seed=3, x=x.tolist(), outer_iters=tr["outer_iters"], inner_
            minor_iters=tr.get("minor_iters", 0), cg_iters=tr.get("cg_iters", 0), breakpoints=tr.get("breakpoints", 0),
            mu=tr["mu"], fixvars_words=[int(w) for w in tr["fixvars_words"]], counters=tr["counters"],
            objective=float(np.sum(P.residuals(x) ** 2)),
-           inner=[dict(k=r["k"], mx=r["mx"], delta=r["delta"], pix=r["pix"], nb_fix=r["nb_fix"], rho=r["rho"], norm_s=r["norm_s"])
+           inner=[{k: r[k] for k in ("k", "mx", "delta", "pix", "nb_fix", "rho", "pred", "norm_s", "omega_tol", "bp_cum", "cg_cum")}
                   for r in tr["inner"]],
            outer=tr["outer"], seconds=time.time() - t0)
 json.dump(out, open(os.path.join(HERE, f"glm_{M}_{n}.json"), "w"))

@@ -168,31 +168,30 @@ def test_native_log_equals_the_oracle_log(S, tmp_path, case):
     assert rel(x_n, x_o) < 1e-10
 
 
-def test_headline_regime_exact_counts_against_golden(S):
-    """cfg3's regime at a size the oracle finishes once on the host (M = 200 000, n = 1024: M/n ~ 200, thousands of Cauchy
-    breakpoints, projected CG never runs): same outer / inner / breakpoint counts, per-iteration AL values to 1e-10, final x
-    to 1e-10, active-set words bit-exact.  Golden: tests/golden/glm_200000_1024.json (tests/golden/make_golden_headline.py)."""
-    path = os.path.join(HERE, "golden", "glm_200000_1024.json")
-    if not os.path.exists(path):
+@pytest.mark.parametrize("M", [200_000, 500_000])
+def test_headline_regime_against_golden(S, M):
+    """cfg3's regime at sizes the oracle finishes once on the host (n = 1024, M/n = 200 and 500: hundreds of Cauchy breakpoints,
+    projected CG all but absent at 5e5): the trajectory against the committed golden (tests/golden/make_golden_headline.py) --
+    exact per-iteration comparison (k, active-set size, cumulative breakpoint / CG counts, AL value, Delta) up to the golden's
+    first noise-driven decision, exact totals / x to 1e-10 / bit-exact active set when it has none (tests/parity.py)."""
+    from tests.parity import assert_trajectory_parity, first_fragile, golden
+    name = f"glm_{M}_1024"
+    if not os.path.exists(os.path.join(HERE, "golden", name + ".json")):
         pytest.skip("golden not generated")
-    g = json.load(open(path))
-    M, n = g["M"], g["n"]
+    g = golden(name)
+    n = g["n"]
     S.set_problem(M, n)
     S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
     x0 = S.model_vectors()["x0"]
     tr = {}
     x, _ = B.tralcnllss(x0, None, None, None, None, None, None, None, None, solver=S, trace=tr)
     st = tr["stats"]
-    assert (tr["outer_iters"], st["inner_iters"], st["minor_iters"], st["cg_iters"], st["breakpoints"]) == \
-           (g["outer_iters"], g["inner_iters"], g["minor_iters"], g["cg_iters"], g["breakpoints"])
-    assert st["breakpoints"] > 500 and st["inc_breakpoints"] == st["breakpoints"]
-    assert rel(x, np.array(g["x"])) < 1e-10
-    assert [int(w) for w in tr["fixvars_words"]] == g["fixvars_words"]
-    for a, b in zip(tr["inner"], g["inner"]):
-        assert a["k"] == b["k"] and a["nb_fix"] == b["nb_fix"]
-        assert abs(a["mx"] - b["mx"]) <= 1e-10 * abs(b["mx"]) and abs(a["delta"] - b["delta"]) <= 1e-10 * b["delta"]
-    obj = S.residuals(x, False)[1]
-    assert abs(obj - g["objective"]) <= 1e-10 * g["objective"]
+    assert st["inc_breakpoints"] == st["breakpoints"] >= 100
+    F = assert_trajectory_parity(name, tr, x, obj_g=S.residuals(x, False)[1])
+    # the well-conditioned part of the solve is most of it: at least 5 inner iterations and 90 % of the AL decrease
+    nprefix = len(g["inner"]) if F is None else F
+    assert nprefix >= 5
+    assert g["inner"][0]["mx"] - g["inner"][nprefix - 1]["mx"] >= 0.9 * (g["inner"][0]["mx"] - g["inner"][-1]["mx"])
 
 
 def test_row_reductions_do_not_depend_on_the_gpu_count(S):
