@@ -85,7 +85,8 @@ int bnl_create(int device, bnl_handle* out) {
     cudaMemset(h->sd, 0, sizeof(Scal));
     memset(h->sh, 0, sizeof(Scal));
     // group mailbox of the row reductions (p2p.h): local until bnl_comm_init maps it into the peers
-    if (cudaMalloc(&h->p2p_buf, p2p_buffer_bytes()) != cudaSuccess || cudaMemset(h->p2p_buf, 0, p2p_buffer_bytes()) != cudaSuccess ||
+    // (>= 4 MB: an allocation of its own, never a sub-allocation of a shared 2 MB block -- it is exported through CUDA IPC)
+    if (cudaMalloc(&h->p2p_buf, p2p_alloc_bytes()) != cudaSuccess || cudaMemset(h->p2p_buf, 0, p2p_alloc_bytes()) != cudaSuccess ||
         cudaMalloc(&h->p2p_counter, 256) != cudaSuccess || cudaMemset(h->p2p_counter, 0, 256) != cudaSuccess) {
         bnl_destroy(h);
         return BNL_EOOM;

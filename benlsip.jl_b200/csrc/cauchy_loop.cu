@@ -63,8 +63,10 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
         const int b = blockIdx.x;
         double theta = 0.0, dind = 0.0;
         long long ind = -1;
+        // a fresh search entered with the literal scalars of its first interval never ran the it == 0 pass that zeroes u
+        const unsigned long long zero_u_at = (a.first && a.use_literal) ? 1ull : ~0ull;
         for (unsigned long long it = 0;; ++it) {
-            const bool skip = (it == 0 && a.use_literal);  // the first decision of a re-entry uses the literal scalars
+            const bool skip = (it == 0 && a.use_literal);  // the first decision of a (re-)entry uses the literal scalars
             if (!skip) {
                 for (int gi = 0; gi < ng; ++gi) {
                     const long long lb = a.geo.local_begin(gi, b), le = a.geo.local_end(gi, b);
@@ -75,7 +77,8 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
                             ui = a.first ? 0.0 : a.u[i];
                             if (a.first) a.u[i] = 0.0;
                         } else {
-                            ui = fma(theta, ti, a.u[i]);
+                            const double u_old = (it == zero_u_at) ? 0.0 : a.u[i];  // u = J s_c = 0 before the first breakpoint
+                            ui = fma(theta, ti, u_old);
                             ti = fma(-dind, __ldg(a.J + (size_t)i * a.ld + ind), ti);
                             a.t[i] = ti;
                             a.u[i] = ui;

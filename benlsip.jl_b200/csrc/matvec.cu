@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) mv_stream_kernel(const MvArgs a) 
 #pragma unroll
                     for (int q = 0; q < RB; ++q) {
                         tsq = fma(t[q], t[q], tsq);
-                        if (MODE == MODE_JV && a.t_out != nullptr && q < rows_valid) a.t_out[row0 + q] = t[q];
+                        if (a.t_out != nullptr && q < rows_valid) a.t_out[row0 + q] = t[q];  // t = J v rows (JV and JTJV modes)
                     }
                 }
             }

@@ -16,7 +16,7 @@ struct MvArgs {
     int ld, R, NS, TG;
     const double* v;   // length ld (zero padded)      [JTJV, JV]
     const double* w;   // length M_loc                 [JTW]
-    double* t_out;     // length M_loc or null         [JV]
+    double* t_out;     // length M_loc or null         [JV, JTJV]: t = J v
     double* partial;   // [ng][G][T][pstride]
     long long pstride;
 };

@@ -40,6 +40,7 @@ inline size_t p2p_buffer_bytes() {
     return p2p_mbox_doubles() * sizeof(double) + (size_t)2 * kP2PMaxRanks * sizeof(unsigned long long) +
            (size_t)2 * kGroups * kLLVals * 2 * sizeof(unsigned long long) + 256;
 }
+inline size_t p2p_alloc_bytes() { return p2p_buffer_bytes() > ((size_t)4 << 20) ? p2p_buffer_bytes() : ((size_t)4 << 20); }
 inline unsigned long long* p2p_flags_of(double* mbox_base) { return reinterpret_cast<unsigned long long*>(mbox_base + p2p_mbox_doubles()); }
 inline unsigned long long* p2p_ll_of(double* mbox_base) { return p2p_flags_of(mbox_base) + 2 * kP2PMaxRanks; }
 

@@ -143,7 +143,7 @@ int form_gram(S* h) {
 
 // ---- AlHessian -------------------------------------------------------------------------------------------
 // Base.:*(H,v) :102-106.  dv: device, length ld.  out: device, length >= ld+1 (out[ld] = ||Jv||^2, global).
-int hess_mul(S* h, const double* dv, double* out) {
+int hess_mul(S* h, const double* dv, double* out, double* t_out) {
     if (!h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound (bnl_eval_jacobian / bnl_upload_jacobian first)");
     if (h->hess_mode == BNL_HESSIAN_GRAM) {
         if (!h->gram_valid) RET(form_gram(h));
@@ -153,7 +153,7 @@ int hess_mul(S* h, const double* dv, double* out) {
     } else {
         {
             EvScope ev(h, 0);
-            CK(mv_launch(MODE_JTJV, h->plan, h->geo, h->J, dv, nullptr, nullptr, h->partial, h->stream));
+            CK(mv_launch(MODE_JTJV, h->plan, h->geo, h->J, dv, nullptr, t_out, h->partial, h->stream));
         }
         KLAUNCH();
         h->st.j_passes += 1;
@@ -395,9 +395,12 @@ double al_value(S* h, double sumsq, const std::vector<double>& y, const std::vec
 }
 
 // ---- cauchy_step :574-639 with the breakpoint loop on the device (cauchy_loop.cu) ---------------------------------
-// t = J d once (one pass), then ONE persistent kernel walks the breakpoints; whenever a number that reaches the iterate is
-// needed (interior minimiser) or a decision is inside the rounding band, Hd = H*d is evaluated literally (:633-635) and
-// the loop is re-entered with those values => the Cauchy point equals the literal search's bit for bit.
+// The first interval is the reference's own: Hd = H*d (:609) in one fused pass that also leaves t = J d in HBM, literal
+// phi', phi'' (:610-611).  A search without breakpoints therefore costs exactly what the literal one costs.  From the first
+// breakpoint on, ONE persistent kernel walks the breakpoints on t = J d, u = J s_c; whenever a number that reaches the
+// iterate is needed (interior minimiser) or a decision is inside the rounding band, Hd = H*d is evaluated literally
+// (:633-635) and the loop is re-entered with those values => the Cauchy point equals the literal search's bit for bit.
+// After a REJECTED step (x, g, J untouched) both Hd and t of the first interval are reused: no pass at all.
 int cauchy_step_incremental(S* h, double delta) {
     VecCtx& c = h->vc;
     if (!h->inc_t) {
@@ -405,27 +408,31 @@ int cauchy_step_incremental(S* h, double delta) {
         CK(cudaMalloc(&h->inc_t, mb));
         CK(cudaMalloc(&h->inc_u, mb));
         CK(cudaMalloc(&h->inc_t0, mb));
+        CK(cudaMalloc(&h->hd0, (size_t)(h->ld + kColAlign) * sizeof(double)));
         CK(cudaMalloc(&h->cl_sync, cauchy_loop_sync_bytes()));
         h->t0_valid = false;
     }
     vk_active_reset(c, c.x, nullptr, h->stream);  // :591
     vk_cauchy_init(c, true, h->stream);           // s_c = 0 ; d = P(-g) :592
     h->st.kernel_launches += 2;
+    const size_t hv_bytes = (size_t)(h->ld + kColAlign) * sizeof(double);
     if (h->t0_valid) {
-        // a rejected step left x, g and J untouched (:358-366): d = P(-g) is the same vector bit for bit, so is t = J d
+        // a rejected step left x, g and J untouched (:358-366): d = P(-g) is the same vector bit for bit, and so are
+        // Hd = H*d (:609) and t = J d -- reuse both instead of a pass over J
         CK(cudaMemcpyAsync(h->inc_t, h->inc_t0, (size_t)h->M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(c.hv, h->hd0, hv_bytes, cudaMemcpyDeviceToDevice, h->stream));
         h->st.t0_reuses++;
+        h->st.hess_mul++;  // logical applies of the reference (:609), no pass here
+        h->st.jv++;
+        h->st.jtw++;
     } else {
-        {   // t = J d  (one J pass; the loop computes ||t||^2 itself, in the chunk geometry)
-            EvScope ev(h, 1);
-            CK(mv_launch(MODE_JV, h->plan, h->geo, h->J, c.d, nullptr, h->inc_t, h->partial, h->stream));
-        }
-        KLAUNCH();
-        h->st.j_passes += 1;
+        RET(hess_mul(h, c.d, c.hv, h->inc_t));  // Hd = H*d :609 -- the fused pass also leaves t = J d in HBM
         CK(cudaMemcpyAsync(h->inc_t0, h->inc_t, (size_t)h->M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->hd0, c.hv, hv_bytes, cudaMemcpyDeviceToDevice, h->stream));
         h->t0_valid = true;
     }
-    h->st.jv++;
+    vk_cauchy_eval(c, delta, h->stream);  // phi', phi'' of the first interval: the literal ones (:610-611)
+    KLAUNCH();
     CauchyLoopArgs a{};
     a.c = c;
     a.geo = h->geo;
@@ -442,7 +449,7 @@ int cauchy_step_incremental(S* h, double delta) {
     a.arrive = h->cl_sync;
     a.bcast = reinterpret_cast<char*>(h->cl_sync) + 64;
     a.first = 1;
-    a.use_literal = 0;
+    a.use_literal = 1;  // the first interval is decided with the literal scalars: a search without breakpoints costs one pass
     for (;;) {
         a.ll_epoch0 = h->ll_epoch;
         CK(cauchy_loop_launch(a, h->prop.multiProcessorCount, h->stream));
@@ -580,7 +587,9 @@ int inner_step(S* h, double delta, double* pred_out) {
     VecCtx& c = h->vc;
     // bound-only problems (mask projection; the loop carries up to kCLMaxP nonlinear-constraint rows itself): device-side
     // breakpoint loop; everything else, and Gram mode (where H*d is an L2-resident gemv anyway): the literal search
-    if (h->cauchy_mode == BNL_CAUCHY_INCREMENTAL && h->mask && h->p <= kCLMaxP && h->hess_mode == BNL_HESSIAN_MATRIX_FREE)
+    // (with several ranks the loop exchanges its two scalars through the peer-mapped LL mailbox: without peer mapping, literal)
+    if (h->cauchy_mode == BNL_CAUCHY_INCREMENTAL && h->mask && h->p <= kCLMaxP && h->hess_mode == BNL_HESSIAN_MATRIX_FREE &&
+        (h->nranks == 1 || h->p2p_on))
         RET(cauchy_step_incremental(h, delta));
     else
         RET(cauchy_step(h, delta));  // :410
@@ -812,7 +821,8 @@ int free_problem(S* h) {
     cudaFree(h->inc_u);
     cudaFree(h->cl_sync);
     cudaFree(h->inc_t0);
-    h->inc_t = h->inc_u = h->inc_t0 = nullptr;
+    cudaFree(h->hd0);
+    h->inc_t = h->inc_u = h->inc_t0 = h->hd0 = nullptr;
     h->t0_valid = false;
     h->cl_sync = nullptr;
     h->gram_ws = nullptr;

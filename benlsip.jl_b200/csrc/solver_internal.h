@@ -99,6 +99,7 @@ struct bnl_solver {
     int cauchy_mode = 0;        // BNL_CAUCHY_LITERAL / BNL_CAUCHY_INCREMENTAL
     double *inc_t = nullptr, *inc_u = nullptr;   // t = J d, u = J s_c (incremental Cauchy search)
     double* inc_t0 = nullptr;                    // J P(-g) of the current (x, g, J): reused by the searches after rejected steps
+    double* hd0 = nullptr;                       // H P(-g) of the same state (n-vector + norm slot)
     bool t0_valid = false;
     unsigned int* cl_sync = nullptr;             // arrive counter + broadcast record of the persistent loop kernel
     double cauchy_guard = 1e-9;                  // relative width of the loop's rounding band
@@ -192,7 +193,7 @@ int resolve_geometry(S* h);
 int alloc_row_buffers(S* h);
 void p2p_local_setup(S* h);
 int form_gram(S* h);
-int hess_mul(S* h, const double* dv, double* out);
+int hess_mul(S* h, const double* dv, double* out, double* t_out = nullptr);  // t_out: also store J v (local rows)
 int vthv_dev(S* h, const double* dv);
 int jtw_dev(S* h, const double* dw, double* out);
 int rebuild_chol(S* h);

