@@ -131,5 +131,13 @@ __host__ __device__ __forceinline__ uint32_t rowkey(uint32_t seed, unsigned long
 __host__ __device__ __forceinline__ uint32_t hash_rc(uint32_t rk, uint32_t j) { return mix32(rk + j * 0x9E3779B9u); }
 __host__ __device__ __forceinline__ double u01(uint32_t h) { return (double)h * 2.3283064365386963e-10; }          // 2^-32
 __host__ __device__ __forceinline__ double usym(uint32_t h) { return (double)h * 4.6566128730773926e-10 - 1.0; }   // 2^-31
+#ifdef __CUDACC__
+// usym(h) without an integer -> FP64 conversion: the double with exponent 0 and mantissa h<<20 is v = 1 + h*2^-32 exactly, and
+// 2 v - 3 = h*2^-31 - 1 exactly (32 fractional bits): bit-identical to usym(), one FMA + two integer ops.
+__device__ __forceinline__ double usym_fast(uint32_t h) {
+    const double v = __hiloint2double((int)(0x3FF00000u | (h >> 12)), (int)(h << 20));
+    return fma(2.0, v, -3.0);
+}
+#endif
 
 }  // namespace bnl

@@ -21,59 +21,84 @@ __device__ __forceinline__ double glm_row_dot(const ModelArgs& a, uint32_t rk, c
         const int j = 2 * c;
         const double2 cs2 = __ldg(reinterpret_cast<const double2*>(a.cs) + c);
         const double2 x2 = __ldg(reinterpret_cast<const double2*>(x) + c);
-        const double a0 = usym(hash_rc(rk, (uint32_t)j)) * cs2.x;
-        const double a1 = usym(hash_rc(rk, (uint32_t)(j + 1))) * cs2.y;
+        const double a0 = usym_fast(hash_rc(rk, (uint32_t)j)) * cs2.x;
+        const double a1 = usym_fast(hash_rc(rk, (uint32_t)(j + 1))) * cs2.y;
         z = fma(a0, x2.x, z);
         z = fma(a1, x2.y, z);
     }
     return warp_sum(z);
 }
 
-// WHAT: 0 setup y, 1 residual (+ sumsq partial), 2 jacobian
-template <int WHAT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) glm_kernel(ModelArgs a, const double* __restrict__ x,
-                                                                const double* __restrict__ yin, double* __restrict__ out,
-                                                                double* __restrict__ J, double* __restrict__ partial) {
-    __shared__ double shd[32];
+// jac_res(x): one warp per row, J_ij = phi'(a_i.x) a_ij written straight to HBM in the row-major panel layout (coalesced 16-byte
+// stores); element-wise, no reduction
+__global__ void __launch_bounds__(kWarpsPerCta * 32) glm_jac_kernel(ModelArgs a, const double* __restrict__ x, double* __restrict__ J) {
     const int lane = threadIdx.x & 31;
-    // WHAT == 1 carries a row reduction (sum r_i^2): CTA (gi, b) owns one row chunk and a warp takes every 8th row of it, so
-    // the partial only depends on chunk-local indices (rowgeom.h).  The element-wise kernels stride over all local rows.
-    long long i0, i1, istep;
-    if (WHAT == 1) {
-        const int cg = blockIdx.x / a.geo.G, cb = blockIdx.x % a.geo.G;
-        i0 = a.geo.local_begin(cg, cb) + (threadIdx.x >> 5);
-        i1 = a.geo.local_end(cg, cb);
-        istep = kWarpsPerCta;
-    } else {
-        i0 = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-        i1 = a.M;
-        istep = (long long)gridDim.x * kWarpsPerCta;
-    }
-    double ss = 0.0;
-    for (long long i = i0; i < i1; i += istep) {
+    const long long i0 = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const long long istep = (long long)gridDim.x * kWarpsPerCta;
+    const int NC = a.ld >> 1;
+    for (long long i = i0; i < a.M; i += istep) {
         const unsigned long long gi = (unsigned long long)(a.row0 + i);
         const uint32_t rk = rowkey(a.seed, gi);
         const double z = glm_row_dot(a, rk, x, lane);
+        const double dphi = 1.0 + 0.1 * cos(z);
+        double2* Jrow = reinterpret_cast<double2*>(J + (size_t)i * a.ld);
+        for (int c = lane; c < NC; c += 32) {
+            const int j = 2 * c;
+            const double2 cs2 = __ldg(reinterpret_cast<const double2*>(a.cs) + c);
+            double2 o;
+            o.x = dphi * (usym_fast(hash_rc(rk, (uint32_t)j)) * cs2.x);
+            o.y = dphi * (usym_fast(hash_rc(rk, (uint32_t)(j + 1))) * cs2.y);
+            Jrow[c] = o;  // padding columns: cs = 0 => exact zeros
+        }
+    }
+}
+
+// ---- GLM residual / data kernels: ONE THREAD PER ROW -----------------------------------------------------------------
+// z_i = a_i . x needs n hashes per row and nothing from memory but x and cs, which every thread of a warp reads at the same j:
+// they sit in shared memory and are broadcast (one LDS per warp and column), the hash and the FMAs run without shuffles.
+// Four interleaved partial sums (columns j mod 4) in fixed order.  WHAT: 0 data y (element-wise), 1 residual + sum of squares
+// per row chunk (CTA (gi, b) owns chunk (gi, b): rowgeom.h).
+template <int WHAT>
+__global__ void __launch_bounds__(256) glm_rows_kernel(ModelArgs a, const double* __restrict__ x, const double* __restrict__ yin,
+                                                       double* __restrict__ out, double* __restrict__ partial) {
+    extern __shared__ double2 sxc[];  // [ld] (x_j, cs_j)
+    __shared__ double shd[32];
+    for (int j = threadIdx.x; j < a.ld; j += blockDim.x) sxc[j] = make_double2(j < a.n ? x[j] : 0.0, a.cs[j]);
+    __syncthreads();
+    long long i0, i1, istep;
+    if (WHAT == 1) {
+        const int cg = blockIdx.x / a.geo.G, cb = blockIdx.x % a.geo.G;
+        i0 = a.geo.local_begin(cg, cb) + threadIdx.x;
+        i1 = a.geo.local_end(cg, cb);
+        istep = blockDim.x;
+    } else {
+        i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        i1 = a.M;
+        istep = (long long)gridDim.x * blockDim.x;
+    }
+    double ss = 0.0;
+    const int n4 = a.ld & ~3;  // ld is a multiple of 16; padding columns have cs = 0
+    for (long long i = i0; i < i1; i += istep) {
+        const unsigned long long gi = (unsigned long long)(a.row0 + i);
+        const uint32_t rk = rowkey(a.seed, gi);
+        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+        uint32_t key = rk;  // rk + j * 0x9E3779B9
+#pragma unroll 2
+        for (int j = 0; j < n4; j += 4) {
+            const double2 p0 = sxc[j], p1 = sxc[j + 1], p2 = sxc[j + 2], p3 = sxc[j + 3];
+            z0 = fma(usym_fast(mix32(key)) * p0.y, p0.x, z0);
+            z1 = fma(usym_fast(mix32(key + 0x9E3779B9u)) * p1.y, p1.x, z1);
+            z2 = fma(usym_fast(mix32(key + 2u * 0x9E3779B9u)) * p2.y, p2.x, z2);
+            z3 = fma(usym_fast(mix32(key + 3u * 0x9E3779B9u)) * p3.y, p3.x, z3);
+            key += 4u * 0x9E3779B9u;
+        }
+        const double z = (z0 + z1) + (z2 + z3);
         if (WHAT == 0) {
-            if (lane == 0) out[i] = z + 0.1 * sin(z) + a.noise * usym(hash_rc(rowkey(a.seed + 1u, gi), 0u));
-        } else if (WHAT == 1) {
-            if (lane == 0) {
-                const double r = z + 0.1 * sin(z) - yin[i];
-                out[i] = r;
-                ss = fma(r, r, ss);
-            }
+            out[i] = z + 0.1 * sin(z) + a.noise * usym(hash_rc(rowkey(a.seed + 1u, gi), 0u));
         } else {
-            const double dphi = 1.0 + 0.1 * cos(z);
-            const int NC = a.ld >> 1;
-            double2* Jrow = reinterpret_cast<double2*>(J + (size_t)i * a.ld);
-            for (int c = lane; c < NC; c += 32) {
-                const int j = 2 * c;
-                const double2 cs2 = __ldg(reinterpret_cast<const double2*>(a.cs) + c);
-                double2 o;
-                o.x = dphi * (usym(hash_rc(rk, (uint32_t)j)) * cs2.x);
-                o.y = dphi * (usym(hash_rc(rk, (uint32_t)(j + 1))) * cs2.y);
-                Jrow[c] = o;  // padding columns: cs = 0 => exact zeros
-            }
+            const double r = z + 0.1 * sin(z) - yin[i];
+            out[i] = r;
+            ss = fma(r, r, ss);
         }
     }
     if (WHAT == 1) {
@@ -157,9 +182,20 @@ int rows_grid(long long M, int nblocks_cap) {
 
 }  // namespace
 
+static cudaError_t glm_rows_smem(size_t bytes) {  // (x_j, cs_j) pairs in shared memory: above 48 KB (n > 3072) needs the opt-in
+    static size_t granted = 48 * 1024;
+    if (bytes <= granted) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(glm_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(glm_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) granted = bytes;
+    return e;
+}
+
 cudaError_t model_setup_y(const ModelArgs& a, const double* x_true, double* y, cudaStream_t st) {
     if (a.model_id == 1) {
-        glm_kernel<0><<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x_true, nullptr, y, nullptr, nullptr);
+        cudaError_t e = glm_rows_smem((size_t)a.ld * sizeof(double2));
+        if (e != cudaSuccess) return e;
+        glm_rows_kernel<0><<<rows_grid(a.M / 32 + 1, 148 * 8), 256, (size_t)a.ld * sizeof(double2), st>>>(a, x_true, nullptr, y, nullptr);
     } else if (a.model_id == 2) {
         expsum_rows_kernel<0><<<rows_grid(a.M / 32 + 1, 148 * 8), 256, 0, st>>>(a, x_true, nullptr, y, nullptr);
     } else {
@@ -171,7 +207,9 @@ cudaError_t model_setup_y(const ModelArgs& a, const double* x_true, double* y, c
 cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y, double* r, double* partial, cudaStream_t st) {
     const int grid = a.geo.ng * a.geo.G;  // one CTA per row chunk; partial[grid] goes through the fixed reduction tree (p2p.h)
     if (a.model_id == 1) {
-        glm_kernel<1><<<grid, kWarpsPerCta * 32, 0, st>>>(a, x, y, r, nullptr, partial);
+        cudaError_t e = glm_rows_smem((size_t)a.ld * sizeof(double2));
+        if (e != cudaSuccess) return e;
+        glm_rows_kernel<1><<<grid, 256, (size_t)a.ld * sizeof(double2), st>>>(a, x, y, r, partial);
     } else if (a.model_id == 2) {
         expsum_rows_kernel<1><<<grid, 256, 0, st>>>(a, x, y, r, partial);
     } else {
@@ -182,7 +220,7 @@ cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y,
 
 cudaError_t model_jacobian(const ModelArgs& a, const double* x, double* J, cudaStream_t st) {
     if (a.model_id == 1) {
-        glm_kernel<2><<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x, nullptr, nullptr, J, nullptr);
+        glm_jac_kernel<<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x, J);
     } else if (a.model_id == 2) {
         expsum_jac_kernel<<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x, J);
     } else {

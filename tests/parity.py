@@ -11,7 +11,7 @@ meaningful (`rho`, `pred`, `mx`, `pix`, `omega_tol`).  `first_fragile(golden)` r
 margin is below the noise threshold; the comparison is
   * EXACT up to that record (k, nb_fix, cumulative breakpoint / CG counts; mx to 1e-10, Delta to 1e-7, pix to 1e-5);
   * if no record is fragile: exact total counts, final x to 1e-10, active-set words bit-exact;
-  * otherwise the end state is compared to the noise floor (objective to 1e-12, x to 2e-8, outer count +-1), and the fragile
+  * otherwise the end state is compared to the noise floor (objective to 1e-12, x to 2e-8, outer count +-2), and the fragile
     record is named in the test output (-rA), so nothing is silently relaxed."""
 import json
 import math
@@ -80,7 +80,7 @@ def assert_trajectory_parity(name, tr_g, x_g, obj_g=None, tol=1e-10, report=prin
         report(f"[parity] {name}: golden is noise-driven from inner record {F} (k={r['k']}, rho={r['rho']:.3g}, "
                f"|ared|={abs(r['rho'] * r['pred']):.2e} vs {64 * EPS * abs(r["mx"]):.2e} noise): exact comparison of the first {F} "
                f"records; counts cuda={counts_g} oracle={counts_o}; x rel diff {rel(x_g, np.array(g['x'])):.2e}")
-        assert abs(counts_g[0] - counts_o[0]) <= 1 and abs(counts_g[1] - counts_o[1]) <= 16
+        assert abs(counts_g[0] - counts_o[0]) <= 2 and abs(counts_g[1] - counts_o[1]) <= 16
         assert rel(x_g, np.array(g["x"])) < 2e-8
         if obj_g is not None:
             assert abs(obj_g - g["objective"]) <= 1e-12 * g["objective"]
