@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
     if (blockIdx.x < (unsigned)G) {
         // ------------------------------------------------ worker ------------------------------------------------
         const int b = blockIdx.x;
+        double* __restrict__ tp = a.t;
+        double* __restrict__ up = a.u;
         double theta = 0.0, dind = 0.0;
         long long ind = -1;
         // a fresh search entered with the literal scalars of its first interval never ran the it == 0 pass that zeroes u
@@ -71,20 +73,49 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
                 for (int gi = 0; gi < ng; ++gi) {
                     const long long lb = a.geo.local_begin(gi, b), le = a.geo.local_end(gi, b);
                     double tt = 0.0, ut = 0.0;
-                    for (long long i = lb + tid; i < le; i += kCLThreads) {
-                        double ti = a.t[i], ui;
-                        if (it == 0) {
-                            ui = a.first ? 0.0 : a.u[i];
-                            if (a.first) a.u[i] = 0.0;
-                        } else {
-                            const double u_old = (it == zero_u_at) ? 0.0 : a.u[i];  // u = J s_c = 0 before the first breakpoint
-                            ui = fma(theta, ti, u_old);
-                            ti = fma(-dind, __ldg(a.J + (size_t)i * a.ld + ind), ti);
-                            a.t[i] = ti;
-                            a.u[i] = ui;
+                    if (it == 0) {
+                        for (long long i = lb + tid; i < le; i += kCLThreads) {
+                            const double ti = tp[i], ui = a.first ? 0.0 : up[i];
+                            if (a.first) up[i] = 0.0;
+                            tt = fma(ti, ti, tt);
+                            ut = fma(ui, ti, ut);
                         }
-                        tt = fma(ti, ti, tt);
-                        ut = fma(ui, ti, ut);
+                    } else {
+                        // u += theta t ; t -= d_ind J[:,ind].  The column read is one 8-byte element per 8 KB row: pure latency,
+                        // so four rows are in flight per thread (loads first, then the arithmetic in row order: the per-thread
+                        // summation order does not depend on the unrolling).
+                        const bool zero_u = (it == zero_u_at);  // u = J s_c = 0 before the first breakpoint
+                        const double* __restrict__ Jc = a.J + ind;
+                        long long i = lb + tid;
+                        for (; i + 3 * kCLThreads < le; i += 4 * kCLThreads) {
+                            double tv[4], uv[4], jv[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const long long r = i + (long long)q * kCLThreads;
+                                tv[q] = tp[r];
+                                uv[q] = zero_u ? 0.0 : up[r];
+                                jv[q] = __ldg(Jc + (size_t)r * a.ld);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const long long r = i + (long long)q * kCLThreads;
+                                const double ui = fma(theta, tv[q], uv[q]);
+                                const double ti = fma(-dind, jv[q], tv[q]);
+                                tp[r] = ti;
+                                up[r] = ui;
+                                tt = fma(ti, ti, tt);
+                                ut = fma(ui, ti, ut);
+                            }
+                        }
+                        for (; i < le; i += kCLThreads) {
+                            const double t0 = tp[i], u0 = zero_u ? 0.0 : up[i];
+                            const double ui = fma(theta, t0, u0);
+                            const double ti = fma(-dind, __ldg(Jc + (size_t)i * a.ld), t0);
+                            tp[i] = ti;
+                            up[i] = ui;
+                            tt = fma(ti, ti, tt);
+                            ut = fma(ui, ti, ut);
+                        }
                     }
                     tt = block_sum(tt, shd);
                     ut = block_sum(ut, shd);
