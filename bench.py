@@ -362,8 +362,11 @@ def run_ours(args, cfg):
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
         if st["cg_iters"] > 0:  # projected CG: time per iteration split into streaming and exposed latency
             hm = st["hess_mul_ms"] / max(st["hess_mul"], 1)
-            line["cg"] = {"iters": st["cg_iters"], "hess_mul_kernel_us": 1e3 * hm,
-                          "note": "one fused J'(Jv) pass + one fused O(n) CG kernel + one host decision per iteration"}
+            line["cg"] = {"iters": st["cg_iters"], "minor_iters": st["minor_iters"], "stream_us_per_iter": 1e3 * hm,
+                          # everything that is not a streaming / generator kernel (reduction tree, fused O(n) CG kernel, host
+                          # decision, launch gaps), spread over the CG + minor iterations: an upper bound of the exposed latency
+                          "exposed_latency_us_per_iter_upper_bound": 1e3 * phases["other_ms"] / max(st["cg_iters"] + st["minor_iters"], 1),
+                          "note": "per CG iteration: one fused J'(Jv) pass + reduction tree + one fused O(n) CG kernel + one host decision"}
         tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if world == 1 and M == CFG["cfg3"]["M"] and n == 1024 and os.path.exists(tp):
             tj = json.load(open(tp))  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
