@@ -49,6 +49,9 @@ CFG = {
     # src/basic_tralcnlss.jl:690-764) carry the solve
     "cfg3cg": dict(M=10_000_000, n=1024, model="glm", seed=3, noise=1e-3, cond_exp=1.0, interior_truth=True),
     "cfg2": dict(M=1_000_000, n=256, model="expsum", seed=1, noise=1e-3, cond_exp=0.0),
+    # BASELINE config[4]: ill-conditioned (column scaling 10^(-6 j/n)), J = 327.7 GB: needs >= 2 GPUs, quoted at 8; the reference
+    # algorithm does not reach its tolerance on it, so it is run with iteration caps (--max-outer / --max-inner)
+    "cfg5": dict(M=10_000_000, n=4096, model="glm", seed=3, noise=1e-3, cond_exp=6.0),
     # BASELINE config[3]: linear equalities + nonlinear (sphere) equality + box, AL loop exercised; general projection
     "cfg4": dict(M=4_000_000, n=2048, model="glm_mixed", m_lin=64, seed=5, noise=1e-3, cond_exp=0.0),
 }
@@ -212,6 +215,10 @@ def make_solver(B, cfg, args, local_rank, world, rank, M):
         S.use_builtin_model(B.MODEL_GLM if cfg["model"] == "glm" else B.MODEL_EXPSUM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
         if cfg.get("interior_truth"):
             S.model_set_truth(interior_truth(n, cfg["seed"]))
+        if args.max_outer:
+            solve_kw["max_outer_iter"] = args.max_outer
+        if args.max_inner:
+            solve_kw["max_inner_iter"] = args.max_inner
     if world > 1:
         init_solver_comm(S)
     return S, n, M_loc, solve_kw
@@ -299,11 +306,14 @@ def run_ours(args, cfg):
               "breakpoints": st["breakpoints"], "hess_mul": st["hess_mul"], "vthv": st["vthv"], "jtw": st["jtw"],
               "jac_eval": st["jac_eval"], "res_eval": st["res_eval"], "j_passes": st["j_passes"],
               "cauchy_loop_launches": st["cauchy_loop_launches"], "cauchy_literal_evals": st["cauchy_literal_evals"],
-              "chol_rebuilds": st["chol_rebuilds"], "allreduces": st["allreduces"], "p2p_allreduces": st["p2p_allreduces"],
+              "chol_rebuilds": st["chol_rebuilds"], "chol_downdates": st["chol_downdates"], "t0_reuses": st["t0_reuses"],
+              "allreduces": st["allreduces"], "p2p_allreduces": st["p2p_allreduces"],
               "mu": tr["mu"]}
     phases = {"streaming_kernels_ms": st["hess_mul_ms"] + st["vthv_ms"] + st["jtw_ms"], "jacobian_generation_ms": st["jac_eval_ms"],
-              "residual_eval_ms": st["res_eval_ms"], "solve_ms": st["solve_ms"]}
-    phases["other_ms"] = phases["solve_ms"] - phases["streaming_kernels_ms"] - phases["jacobian_generation_ms"] - phases["residual_eval_ms"]
+              "residual_eval_ms": st["res_eval_ms"], "gram_formation_ms": st["gram_ms"], "projection_factor_ms": st["chol_ms"],
+              "solve_ms": st["solve_ms"]}
+    phases["other_ms"] = (phases["solve_ms"] - phases["streaming_kernels_ms"] - phases["jacobian_generation_ms"] - phases["residual_eval_ms"]
+                          - phases["gram_formation_ms"] - phases["projection_factor_ms"])
 
     # ---- extras, reported beside (never inside) the headline ----
     extras = {}
@@ -347,7 +357,7 @@ def run_ours(args, cfg):
                            "collective": ("NVLink peer-memory exchange of per-group sums" if S.comm_info()["p2p_allreduce"] else ("ncclAllGather of per-group sums" if world > 1 else "none")),
                            "l2": f"no flush needed: the J shard streamed by every pass is {8.0 * M_loc * n / 1e9:.1f} GB >> 126 MB L2",
                            "step": "one full tralcnllss solve to the reference tolerances (defaults), outer loop on the host, subproblems through the C ABI",
-                           "hessian": args.hessian, "cauchy": args.cauchy},
+                           "hessian": args.hessian, "cauchy": args.cauchy, "iteration_caps": solve_kw or None},
                 "counts": counts, "phases_ms_last_step": phases,
                 "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"])),
                           "x_crc": int(np.frombuffer(x.tobytes(), dtype=np.uint64).sum() & np.uint64(0xFFFFFFFFFFFF))},

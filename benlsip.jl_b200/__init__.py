@@ -71,7 +71,8 @@ class Stats(C.Structure):
                [(k, C.c_double) for k in ("hess_mul_ms", "vthv_ms", "jtw_ms", "res_eval_ms", "jac_eval_ms", "solve_ms")] + \
                [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double),
                 ("p2p_allreduces", C.c_int64), ("inc_breakpoints", C.c_int64), ("cauchy_loop_launches", C.c_int64),
-                ("cauchy_literal_evals", C.c_int64), ("t0_reuses", C.c_int64)]
+                ("cauchy_literal_evals", C.c_int64), ("t0_reuses", C.c_int64), ("chol_downdates", C.c_int64),
+                ("chol_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

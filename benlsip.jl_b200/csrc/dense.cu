@@ -238,6 +238,42 @@ __global__ void k_rs_rebuild(DenseCtx c, const unsigned char* fix) {
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) d[i] = s[i];
 }
 
+// One variable left the free set (add_active!(ind), src/polyhedral_constraints.jl:240-249): A_free A_free' loses the rank-one
+// term a a' with a = A[:,ind], so its Cholesky factor is DOWNDATED in O(m^2) (hyperbolic rotations, LINPACK dchdd) instead of
+// being rebuilt from the O(m^2 n) products -- the reference rebuilds its (m+q)^2 factor from scratch here and flags the cost
+// itself (:51).  One warp; `ind` is read from the device scalars of the scan that chose the breakpoint.
+__global__ void k_rs_downdate(DenseCtx c) {
+    const int m = c.m, lane = threadIdx.x;
+    const long long ind = c.sd->bp_ind;
+    double* a = c.ywork;  // m-vector workspace
+    if (ind >= 0) {
+        for (int i = lane; i < m; i += 32) a[i] = c.A[(size_t)i * c.ld + ind];
+        __syncwarp();
+        for (int k = 0; k < m; ++k) {
+            const double lkk = c.Lr[(size_t)k * m + k], ak = a[k];
+            const double r2 = lkk * lkk - ak * ak;
+            if (!(r2 > 0.0)) {  // A_free lost full row rank: PosDefException in the reference (:57)
+                if (lane == 0) c.sd->chol_fail = 1;
+                break;
+            }
+            const double r = sqrt(r2), cc = r / lkk, ss = ak / lkk;
+            __syncwarp();
+            if (lane == 0) c.Lr[(size_t)k * m + k] = r;
+            for (int i = k + 1 + lane; i < m; i += 32) {
+                const double lik = (c.Lr[(size_t)k * m + i] - ss * a[i]) / cc;
+                c.Lr[(size_t)k * m + i] = lik;
+                a[i] = cc * a[i] - ss * lik;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    const int nwords = sizeof(Scal) / 8;
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(c.sd);
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(c.sh);
+    for (int i = lane; i < nwords; i += 32) d[i] = s[i];
+}
+
 __global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double* r, double* v, int negate) {
     const int m = c.m;
     const double sgn = negate ? -1.0 : 1.0;
@@ -288,6 +324,7 @@ __global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double*
 void dk_left_mul(const DenseCtx& c, const double* x, double* y, cudaStream_t st) { k_left_mul<<<1, kDT, 0, st>>>(c, x, y); }
 void dk_left_mul_tr(const DenseCtx& c, const double* y, double* x, cudaStream_t st) { k_left_mul_tr<<<1, kDT, 0, st>>>(c, y, x); }
 void dk_rs_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st) { k_rs_rebuild<<<1, kDT, 0, st>>>(c, fix); }
+void dk_rs_downdate(const DenseCtx& c, cudaStream_t st) { k_rs_downdate<<<1, 32, 0, st>>>(c); }
 void dk_rs_project(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, bool negate, cudaStream_t st) {
     k_rs_project<<<1, kDT, 0, st>>>(c, fix, r, v, negate ? 1 : 0);
 }

@@ -37,6 +37,8 @@ void dk_left_mul_tr(const DenseCtx& c, const double* y, double* x, cudaStream_t 
 // reference's O(q^3) rebuild, src/polyhedral_constraints.jl:51 flags that cost).  Same mathematics, same failure
 // condition (A_free rank deficient <=> PosDefException), different rounding.
 void dk_rs_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st);
+// the variable sd->bp_ind just left the free set: rank-one downdate of the m x m factor, O(m^2)
+void dk_rs_downdate(const DenseCtx& c, cudaStream_t st);
 void dk_rs_project(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, bool negate, cudaStream_t st);
 
 }  // namespace bnl

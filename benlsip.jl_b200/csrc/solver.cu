@@ -28,6 +28,7 @@ int sync(S* h) {
                 case 3: h->st.res_eval_ms += ms; break;
                 case 4: h->st.jac_eval_ms += ms; break;
                 case 5: h->st.gram_ms += ms; break;
+                case 6: h->st.chol_ms += ms; break;
             }
             h->ev_free.push_back(e);
             h->ev_busy[i] = h->ev_busy.back();
@@ -213,12 +214,24 @@ int jtw_dev(S* h, const double* dw, double* out) {
 // ---- projection / active set (general path hooks) --------------------------------------------------------
 int rebuild_chol(S* h) {  // update_chol! :62-68 (general path only; for m_lin == 0 the factor is I: nothing to do)
     if (h->mask) return BNL_OK;
+    EvScope ev(h, 6);
     if (h->literal_proj)
         dk_rebuild(h->dc, h->vc.fix, h->stream);  // the reference's (m+q)^2 block factor, O(q^3)
     else
         dk_rs_rebuild(h->dc, h->vc.fix, h->stream);  // m x m factor of A_free A_free' (dense.h)
     KLAUNCH();
     h->st.chol_rebuilds++;
+    return BNL_OK;
+}
+// add_active!(lincons, chol_aat, ind) for the breakpoint variable sd->bp_ind: O(m^2) downdate of the reduced-space factor
+// (the literal block factor, BNL_LITERAL_PROJECTION=1, is rebuilt as in the reference)
+int downdate_chol(S* h) {
+    if (h->mask) return BNL_OK;
+    if (h->literal_proj) return rebuild_chol(h);
+    EvScope ev(h, 6);
+    dk_rs_downdate(h->dc, h->stream);
+    KLAUNCH();
+    h->st.chol_downdates++;
     return BNL_OK;
 }
 int check_chol(S* h) {  // after a sync
@@ -507,7 +520,7 @@ int cauchy_step(S* h, double delta) {
             if (h->sh->bp_ind < 0) return h->fail(BNL_EBOUNDS, "BoundsError: next_breakpoint found no breakpoint (ind = -1)");
             vk_cauchy_advance(c, h->mask, 1, h->stream);  // :628-632
             KLAUNCH();
-            RET(rebuild_chol(h));
+            RET(downdate_chol(h));  // add_active!(ind): one column leaves A_free
             if (!h->mask) RET(project_general(h, c.g, c.d, true));
             RET(hess_mul(h, c.d, c.hv));  // :633
             vk_cauchy_eval(c, delta, h->stream);

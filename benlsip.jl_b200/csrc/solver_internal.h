@@ -197,6 +197,7 @@ int hess_mul(S* h, const double* dv, double* out, double* t_out = nullptr);  // 
 int vthv_dev(S* h, const double* dv);
 int jtw_dev(S* h, const double* dw, double* out);
 int rebuild_chol(S* h);
+int downdate_chol(S* h);
 int check_chol(S* h);
 int project_general(S* h, const double* src, double* dst, bool negate);
 bnl::ModelArgs margs(S* h);

@@ -89,6 +89,8 @@ typedef struct bnl_stats {
     int64_t cauchy_loop_launches; /* launches of the persistent breakpoint-loop kernel                               */
     int64_t cauchy_literal_evals; /* literal Hd = H*d evaluations the guarded loop asked for (:633-635)              */
     int64_t t0_reuses;            /* Cauchy searches after a rejected step that reused t = J P(-g) instead of a J pass */
+    int64_t chol_downdates;       /* O(m^2) rank-one downdates of the projection factor (one per Cauchy breakpoint, m_lin > 0) */
+    double chol_ms;               /* CUDA-event time of the factor rebuilds + downdates                                */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */

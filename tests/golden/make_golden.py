@@ -33,13 +33,13 @@ cases = {
 for name, (P, kw) in cases.items():
     json.dump(run(P, **kw), open(os.path.join(HERE, name + ".json"), "w"))
     print("wrote", name)
-# cfg5 family (ill-conditioned): three consecutive inner steps from x0 (Cauchy point + projected CG), per-step quantities
+# cfg5 family (ill-conditioned): twelve consecutive inner steps from x0 (Cauchy point + projected CG), per-step quantities
 P = GlmProblem(3000, 96, seed=3, cond_exp=6.0)
 L0 = O._cholesky_lower(np.zeros((0, 0)))
 cons = O.MixedConstraints(P.A, L0, l=P.xlow, u=P.xupp)
 x = P.x0.copy()
 steps = []
-for it in range(3):
+for it in range(12):
     J, r = P.jac_res(x), P.residuals(x)
     g = J.T @ r
     H = O.AlHessian(J, np.zeros((0, 96)), 0.0)

@@ -52,12 +52,29 @@ t_apply = (time.perf_counter() - t0) / 20
 st = S.stats()
 S.set_hessian_mode(B.HESSIAN_MATRIX_FREE)
 hv_mf = S.hess_mul(v)
+# same-run FP64 tensor ceiling: cuBLAS DGEMM A'A (n x K x n, K rows of an FP64 matrix resident in HBM), best of 3, CUDA events
+K = min(m_loc, 2_000_000_000 // (8 * n) * 4)  # <= 8 GB operand
+Ad = torch.randn(K, n, dtype=torch.float64, device="cuda")
+best = float("inf")
+for _ in range(4):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    Gd = Ad.t() @ Ad
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1))
+dgemm_tflops = 2.0 * K * n * n / (best * 1e-3) / 1e12
+del Ad, Gd
 vals = torch.tensor([ms_kernel, t_gram_total, ms_jtjv], dtype=torch.float64, device="cuda")
 if world > 1:
     dist.all_reduce(vals, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"workload": "cfg5 gram", "M": M, "n": n, "n_gpus": world, "rows_per_gpu": m_loc, "cond_exp": args.cond_exp,
                       "gram_kernel_ms": float(vals[0]), "gram_tflops_issued_per_gpu": flops / float(vals[0]) / 1e9,
+                      "gram_tflops_2Mn2_equiv_per_gpu": 2.0 * m_loc * n * n / float(vals[0]) / 1e9,
+                      "cublas_dgemm_tflops_same_run": dgemm_tflops, "cublas_dgemm_shape": [n, K, n],
+                      "gram_issued_over_dgemm": flops / float(vals[0]) / 1e9 / dgemm_tflops,
+                      "gram_2Mn2_equiv_over_dgemm": 2.0 * m_loc * n * n / float(vals[0]) / 1e9 / dgemm_tflops,
                       "gram_tflops_issued_total": world * flops / float(vals[0]) / 1e9,
                       "gram_plus_allreduce_wall_ms": 1e3 * float(vals[1]), "allreduce_bytes": 8 * ((n + 15) // 16 * 16) ** 2,
                       "gram_apply_device_ms": st["hess_mul_ms"] / max(st["hess_mul"], 1), "gram_apply_abi_wall_ms": 1e3 * t_apply,
