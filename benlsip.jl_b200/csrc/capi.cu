@@ -95,6 +95,8 @@ int bnl_create(int device, bnl_handle* out) {
     {
         const char* env = getenv("BNL_CAUCHY");
         h->cauchy_mode = (env && env[0] == 'l') ? BNL_CAUCHY_LITERAL : BNL_CAUCHY_INCREMENTAL;
+        const char* fj = getenv("BNL_FUSE_JTR");
+        h->fuse_jtr = !(fj && fj[0] == '0');
         const char* gd = getenv("BNL_CAUCHY_GUARD");
         if (gd && atof(gd) > 0.0) h->cauchy_guard = atof(gd);
     }
@@ -963,7 +965,7 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
     ENTER();
     if (reps < 1) return BNL_EINVAL;
     if (kind <= 2 && !h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
-    if ((kind == 3 || kind == 4) && h->model_id == 0) return h->fail(BNL_EINVAL, "builtin model needed");
+    if ((kind == 3 || kind == 4 || kind == 6) && h->model_id == 0) return h->fail(BNL_EINVAL, "builtin model needed");
     if (kind == 5 && !h->have_J) return h->fail(BNL_EINVAL, "no Jacobian bound");
     const double Jbytes = 8.0 * (double)h->M * (double)h->ld;
     double bytes = 0.0;
@@ -994,6 +996,12 @@ int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, do
                 break;
             case 4:
                 CK(model_jacobian(margs(h), h->vc.x, h->J, h->stream));
+                bytes = Jbytes;
+                break;
+            case 6:  // Jacobian generation fused with J'r (GLM, ld <= 1024)
+                if (!(h->model_id == BNL_MODEL_GLM && h->plan.warp_team && h->plan.T == 8)) return h->fail(BNL_EINVAL, "fused generator: GLM with ld <= 1024");
+                CK(model_jacobian_jtr(margs(h), h->vc.x, h->r, h->J, h->partial, h->plan.pstride, h->plan.KCH, h->plan.RB, h->stream));
+                RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, 0, h->ld, h->vc.t1));
                 bytes = Jbytes;
                 break;
             case 5:

@@ -53,6 +53,57 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) glm_jac_kernel(ModelArgs a,
     }
 }
 
+// jac_res(x) FUSED with J'r (first_derivatives, src/basic_tralcnlss.jl:72-74: g = Jx'*rx right after Jx = jac_res(x)): while a
+// row of J is still in registers its contribution r_i J_i. is accumulated, so the accepted step does not stream the 8*M*n bytes
+// back in.  The kernel walks the rows exactly like the streaming J'w kernel (matvec.cu, MODE_JTW): CTA b owns the chunks (g, b),
+// warp w of 8 takes the RB-row stages w, w+8, ... of a chunk, lane u owns the double2 column chunks u + 32k, and acc += J*r is
+// the same FMA in the same order -- the partials, and therefore g, are BIT-IDENTICAL to the unfused pass (tested).
+template <int KCH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) glm_jac_jtr_kernel(ModelArgs a, const double* __restrict__ x,
+                                                                        const double* __restrict__ r, double* __restrict__ J,
+                                                                        double* __restrict__ partial, long long pstride, int RB) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cg = blockIdx.x / a.geo.G, cb = blockIdx.x % a.geo.G;
+    const long long lb = a.geo.local_begin(cg, cb), le = a.geo.local_end(cg, cb);
+    const long long nst = (le - lb + RB - 1) / RB;
+    const int NC = a.ld >> 1;
+    double2 acc[KCH];
+#pragma unroll
+    for (int k = 0; k < KCH; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (long long st = warp; st < nst; st += kWarpsPerCta) {
+        for (int q = 0; q < RB; ++q) {
+            const long long i = lb + st * RB + q;
+            if (i >= le) break;
+            const unsigned long long gi = (unsigned long long)(a.row0 + i);
+            const uint32_t rk = rowkey(a.seed, gi);
+            const double z = glm_row_dot(a, rk, x, lane);  // same arithmetic as glm_jac_kernel
+            const double dphi = 1.0 + 0.1 * cos(z);
+            const double ri = __ldg(r + i);
+            double2* Jrow = reinterpret_cast<double2*>(J + (size_t)i * a.ld);
+#pragma unroll
+            for (int k = 0; k < KCH; ++k) {
+                const int c = lane + 32 * k;
+                if (c < NC) {
+                    const int j = 2 * c;
+                    const double2 cs2 = __ldg(reinterpret_cast<const double2*>(a.cs) + c);
+                    double2 o;
+                    o.x = dphi * (usym_fast(hash_rc(rk, (uint32_t)j)) * cs2.x);
+                    o.y = dphi * (usym_fast(hash_rc(rk, (uint32_t)(j + 1))) * cs2.y);
+                    Jrow[c] = o;
+                    acc[k].x = fma(o.x, ri, acc[k].x);
+                    acc[k].y = fma(o.y, ri, acc[k].y);
+                }
+            }
+        }
+    }
+    double* pout = partial + ((size_t)blockIdx.x * kWarpsPerCta + warp) * pstride;  // [gi][b][team = warp][*]
+#pragma unroll
+    for (int k = 0; k < KCH; ++k) {
+        const int c = lane + 32 * k;
+        if (c < NC) reinterpret_cast<double2*>(pout)[c] = acc[k];
+    }
+}
+
 // ---- GLM residual / data kernels: ONE THREAD PER ROW -----------------------------------------------------------------
 // z_i = a_i . x needs n hashes per row and nothing from memory but x and cs, which every thread of a warp reads at the same j:
 // they sit in shared memory and are broadcast (one LDS per warp and column), the hash and the FMAs run without shuffles.
@@ -225,6 +276,22 @@ cudaError_t model_jacobian(const ModelArgs& a, const double* x, double* J, cudaS
         expsum_jac_kernel<<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x, J);
     } else {
         return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// jac_res(x) with the J'r partials of the row-chunk geometry (GLM, ld <= 1024): partial[ng][G][8][pstride], columns [0, ld)
+cudaError_t model_jacobian_jtr(const ModelArgs& a, const double* x, const double* r, double* J, double* partial, long long pstride,
+                               int KCH, int RB, cudaStream_t st) {
+    if (a.model_id != 1) return cudaErrorInvalidValue;
+    const int grid = a.geo.ng * a.geo.G;
+    switch (KCH) {
+        case 1: glm_jac_jtr_kernel<1><<<grid, kWarpsPerCta * 32, 0, st>>>(a, x, r, J, partial, pstride, RB); break;
+        case 2: glm_jac_jtr_kernel<2><<<grid, kWarpsPerCta * 32, 0, st>>>(a, x, r, J, partial, pstride, RB); break;
+        case 4: glm_jac_jtr_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(a, x, r, J, partial, pstride, RB); break;
+        case 8: glm_jac_jtr_kernel<8><<<grid, kWarpsPerCta * 32, 0, st>>>(a, x, r, J, partial, pstride, RB); break;
+        case 16: glm_jac_jtr_kernel<16><<<grid, kWarpsPerCta * 32, 0, st>>>(a, x, r, J, partial, pstride, RB); break;
+        default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

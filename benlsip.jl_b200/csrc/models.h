@@ -24,4 +24,9 @@ cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y,
 // J (row-major M x ld, zero padded) = d model / d x at x
 cudaError_t model_jacobian(const ModelArgs& a, const double* x, double* J, cudaStream_t st);
 
+// GLM only, ld <= 1024: the same J, plus the per-(chunk, warp) partials of J'r in the layout of the streaming kernels' partials
+// (KCH, RB = the streaming plan's): finishing them with group_reduce / group_sum gives g = J'r bit-identical to a J'w pass.
+cudaError_t model_jacobian_jtr(const ModelArgs& a, const double* x, const double* r, double* J, double* partial, long long pstride,
+                               int KCH, int RB, cudaStream_t st);
+
 }  // namespace bnl

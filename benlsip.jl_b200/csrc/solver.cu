@@ -347,12 +347,24 @@ int upload_colmajor(S* h, const double* src, long long rows, int cols, long long
 }
 
 // jac_res(x), jac_nlcons(x): fills J (and C in callback mode)
-int eval_jacobian(S* h, const double* dx) {
+int eval_jacobian(S* h, const double* dx, const double* r_for_gradient) {
+    h->jtr_valid = false;
     if (h->model_id != 0) {
+        // first_derivatives (:72-74) computes Jx'*rx right after Jx: when the residual of this x is at hand the GLM generator
+        // accumulates J'r while it writes J (bit-identical to a separate J'w pass) and the pass is not streamed back in
+        const bool fuse = r_for_gradient != nullptr && h->fuse_jtr && h->model_id == BNL_MODEL_GLM && h->plan.warp_team && h->plan.T == 8;
         {
             EvScope ev(h, 4);
-            CK(model_jacobian(margs(h), dx, h->J, h->stream));
+            if (fuse)
+                CK(model_jacobian_jtr(margs(h), dx, r_for_gradient, h->J, h->partial, h->plan.pstride, h->plan.KCH, h->plan.RB, h->stream));
+            else
+                CK(model_jacobian(margs(h), dx, h->J, h->stream));
             KLAUNCH();
+        }
+        if (fuse) {
+            RET(row_reduce(h, h->partial, h->plan.T, h->plan.pstride, 0, h->ld, h->vc.hv));
+            h->jtr_valid = true;
+            h->st.fused_jtr++;
         }
         if (h->p > 0) {  // built-in jac_nlcons(x)
             if (h->nl_kind != BNL_NLCONS_SPHERE) return h->fail(BNL_EINVAL, "p > 0 with a built-in model needs bnl_use_builtin_nlcons");
@@ -387,7 +399,12 @@ int eval_jacobian(S* h, const double* dx) {
 // g = Jx'*rx + Cx'*y_bar  (:45, :74)
 int gradient(S* h, const double* rbuf, const std::vector<double>& ybar) {
     h->t0_valid = false;
-    RET(jtw_dev(h, rbuf, h->vc.hv));
+    if (h->jtr_valid) {  // J'r came out of the Jacobian generation (eval_jacobian): no pass
+        h->jtr_valid = false;
+        h->st.jtw++;
+    } else {
+        RET(jtw_dev(h, rbuf, h->vc.hv));
+    }
     CK(cudaMemcpyAsync(h->vc.g, h->vc.hv, (size_t)h->ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (h->p > 0) {
         RET(put_vec(h, ybar.data(), h->vc.pvec, h->p));
@@ -668,7 +685,7 @@ int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out) {
     VecCtx& c = h->vc;
     h->vc.mu = mu;
     RET(eval_residual(h, c.x, h->r, h->h_cx));
-    RET(eval_jacobian(h, c.x));
+    RET(eval_jacobian(h, c.x, h->r));
     if (h->p > 0) {
         vk_scale_C(h->vc, h->stream);
         KLAUNCH();
@@ -731,7 +748,7 @@ int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double o
             std::swap(h->r, h->r_trial);
             h->h_cx = h->h_cx_next;
             mx = mx_next;
-            RET(eval_jacobian(h, c.x));  // first_derivatives :72
+            RET(eval_jacobian(h, c.x, h->r));  // first_derivatives :72 (+ the J'r of :74 on the fly)
             for (int i = 0; i < h->p; ++i) h->h_ybar[i] = y[i] + mu * h->h_cx[i];
             RET(gradient(h, h->r, h->h_ybar));  // :74
         }

@@ -101,6 +101,8 @@ struct bnl_solver {
     double* inc_t0 = nullptr;                    // J P(-g) of the current (x, g, J): reused by the searches after rejected steps
     double* hd0 = nullptr;                       // H P(-g) of the same state (n-vector + norm slot)
     bool t0_valid = false;
+    bool jtr_valid = false;                      // hv = J'r of the Jacobian just generated (fused generator)
+    bool fuse_jtr = true;                        // BNL_FUSE_JTR=0 disables the fused generator
     unsigned int* cl_sync = nullptr;             // arrive counter + broadcast record of the persistent loop kernel
     double cauchy_guard = 1e-9;                  // relative width of the loop's rounding band
     bool hv_holds_Hs = false;                    // hv = H*s of the CURRENT s (its slot [ld] = ||J s||^2): vthv(s) is free
@@ -203,7 +205,7 @@ int project_general(S* h, const double* src, double* dst, bool negate);
 bnl::ModelArgs margs(S* h);
 int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_out);
 int upload_colmajor(S* h, const double* src, long long rows, int cols, long long lds, double* dst_rowmajor, int ldd);
-int eval_jacobian(S* h, const double* dx);
+int eval_jacobian(S* h, const double* dx, const double* r_for_gradient = nullptr);  // r given: J'r is accumulated on the fly
 int gradient(S* h, const double* rbuf, const std::vector<double>& ybar);
 int cauchy_step(S* h, double delta);
 int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool apply_linesearch_and_accumulate, bool bounds_given);

@@ -91,6 +91,7 @@ typedef struct bnl_stats {
     int64_t t0_reuses;            /* Cauchy searches after a rejected step that reused t = J P(-g) instead of a J pass */
     int64_t chol_downdates;       /* O(m^2) rank-one downdates of the projection factor (one per Cauchy breakpoint, m_lin > 0) */
     double chol_ms;               /* CUDA-event time of the factor rebuilds + downdates                                */
+    int64_t fused_jtr;            /* Jacobian generations that produced J'r on the fly (no J'w pass for the gradient)  */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */
@@ -221,7 +222,8 @@ int bnl_reset_stats(bnl_handle h);
 int bnl_get_inner_log(bnl_handle h, bnl_inner_record* out, int32_t capacity, int32_t* count);
 /* Device-side microbenchmarks for the roofline report: `reps` back-to-back launches of one kernel class
  * timed with CUDA events on the library's stream; kind: 0 fused J'(Jv), 1 Jv (norm only), 2 J'w,
- * 3 residual eval, 4 Jacobian generation, 5 Gram (DMMA; FLOPs are returned in bytes_per_launch).
+ * 3 residual eval, 4 Jacobian generation, 5 Gram (DMMA; FLOPs are returned in bytes_per_launch), 6 Jacobian generation fused
+ * with J'r (GLM, n <= 1024).
  * Returns average ms per launch and algorithmic bytes per launch. */
 int bnl_time_kernel(bnl_handle h, int32_t kind, int32_t reps, double* avg_ms, double* bytes_per_launch);
 int bnl_device_info(bnl_handle h, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* free_bytes,

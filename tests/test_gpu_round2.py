@@ -242,3 +242,34 @@ def test_row_reductions_do_not_depend_on_the_gpu_count(S):
         else:
             for a, b in zip(acc, ref):
                 assert rel(a, b) < 1e-14
+
+
+@pytest.mark.parametrize("M,n", [(30_000, 1024), (9_001, 250), (5_000, 64), (4_096, 24)])
+def test_fused_jacobian_gradient_is_bit_identical(M, n):
+    """first_derivatives (:72-74): g = Jx'*rx right after Jx = jac_res(x).  The GLM generator accumulates J'r while it writes J,
+    in the streaming J'w kernel's own row / lane / FMA order: the gradient, the AL value and the whole solve must be bitwise
+    what the separate pass gives (BNL_FUSE_JTR=0), in every tiling regime (KCH, RB)."""
+    import os
+    res = []
+    for fuse in ("1", "0"):
+        os.environ["BNL_FUSE_JTR"] = fuse
+        try:
+            T = B.Solver(0)
+        finally:
+            del os.environ["BNL_FUSE_JTR"]
+        T.set_problem(M, n)
+        T.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+        x = np.linspace(-0.3, 0.3, n)
+        mx, g, _ = T.new_point(x, None, 10.0)
+        st = T.stats()
+        tr = {}
+        xs, _ = B.tralcnllss(T.model_vectors()["x0"], None, None, None, None, None, None, None, None, solver=T, trace=tr)
+        res.append((mx, g, xs, tr["outer_iters"], tr["stats"]["inner_iters"], st["fused_jtr"], tr["stats"]["j_passes"]))
+        # and the Jacobian itself is the same matrix
+        v = np.cos(np.arange(n))
+        res[-1] += (T.hess_mul(v),)
+        T.close()
+    a, b = res
+    assert a[5] >= 1 and b[5] == 0 and a[6] < b[6]
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3:5] == b[3:5]
+    assert np.array_equal(a[7], b[7])

@@ -21,7 +21,7 @@ for M, n in cases:
     S.eval_jacobian(x0 + 0.1)
     S.residuals(x0 + 0.1, False)
     out = {"M": M, "n": n}
-    for kind, name in [(0, "jtjv"), (1, "jv"), (2, "jtw"), (3, "residual"), (4, "jacobian")]:
+    for kind, name in [(0, "jtjv"), (1, "jv"), (2, "jtw"), (3, "residual"), (4, "jacobian")] + ([(6, "jacobian_fused_jtr")] if n <= 1024 else []):
         ms, nbytes = S.time_kernel(kind, 20)
         out[name] = {"ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1)}
     ms, fl = S.time_kernel(5, 3)
