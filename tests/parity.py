@@ -66,7 +66,9 @@ def assert_trajectory_parity(name, tr_g, x_g, obj_g=None, tol=1e-10, report=prin
         # Delta_0 = 0.1 ||g|| and pix = ||P(-g)|| inherit the cancellation in g = J'r + C'(y + mu c) (mu up to 1e9 on the
         # mixed-constraint family): compared to 1e-7 / 1e-5, the AL value itself to `tol`
         assert abs(a["delta"] - b["delta"]) <= 1e-7 * abs(b["delta"]), (i, a, b)
-        assert abs(a["pix"] - b["pix"]) <= 1e-5 * abs(b["pix"]) + 1e-12, (i, a, b)
+        # (pix is only ever compared with omega_tol / crit_tol: a criticality measure that is pure rounding residue, far below
+        # the tolerance it is tested against, is compared on that scale)
+        assert abs(a["pix"] - b["pix"]) <= 1e-5 * abs(b["pix"]) + 1e-6 * b["omega_tol"] + 1e-12, (i, a, b)
     counts_g = (tr_g["outer_iters"], st["inner_iters"], st["minor_iters"], st["cg_iters"], st["breakpoints"])
     counts_o = (g["outer_iters"], g["inner_iters"], g["minor_iters"], g["cg_iters"], g["breakpoints"])
     if F is None:

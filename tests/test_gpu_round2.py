@@ -273,3 +273,24 @@ def test_fused_jacobian_gradient_is_bit_identical(M, n):
     assert a[5] >= 1 and b[5] == 0 and a[6] < b[6]
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3:5] == b[3:5]
     assert np.array_equal(a[7], b[7])
+
+
+def test_cfg4_family_mid_size_against_golden(S):
+    """cfg4 family (linear equalities + sphere constraint + box) at M = 4000, n = 64, m_lin = 8 through the device path: 684
+    inner iterations, 32 667 Cauchy breakpoints -- each one a rank-one DOWNDATE of the projection factor (csrc/dense.cu) where
+    the reference rebuilds its (m+q)^2 factor (src/polyhedral_constraints.jl:62-68) -- mu from 10 to 1e11.  Trajectory against
+    the oracle's golden (which uses the literal block factor): tests/parity.py criterion."""
+    from tests.parity import assert_trajectory_parity, golden
+    g = golden("mixed_4000_64_8")
+    P = MixedConstraintProblem(g["M"], g["n"], g["m_lin"])
+    S.set_problem(P.M, P.n, P.A, P.xlow, P.xupp, p=1)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, P.seed)
+    S.model_set_truth(P.x_star, P.x0)
+    S.use_builtin_nlcons(B.NLCONS_SPHERE, P.rho2)
+    tr = {}
+    x, y = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr, max_outer_iter=60, max_inner_iter=200)
+    st = tr["stats"]
+    assert st["chol_downdates"] == st["breakpoints"] > 10_000
+    F = assert_trajectory_parity("mixed_4000_64_8", tr, x)
+    assert (F is None or F >= 100) and tr["mu"] == g["mu"]
+    assert abs(P.nlconstraints(x)[0]) < 1e-8 and np.max(np.abs(P.A @ x - P.b)) < 1e-12
