@@ -97,6 +97,8 @@ int bnl_create(int device, bnl_handle* out) {
         h->cauchy_mode = (env && env[0] == 'l') ? BNL_CAUCHY_LITERAL : BNL_CAUCHY_INCREMENTAL;
         const char* fj = getenv("BNL_FUSE_JTR");
         h->fuse_jtr = !(fj && fj[0] == '0');
+        const char* gg = getenv("BNL_GRAM_GUARD");
+        if (gg && atof(gg) > 0.0) h->gram_guard = atof(gg);
         const char* gd = getenv("BNL_CAUCHY_GUARD");
         if (gd && atof(gd) > 0.0) h->cauchy_guard = atof(gd);
     }

@@ -42,6 +42,7 @@ struct Scal {
     // persistent Cauchy breakpoint loop (cauchy_loop.cu)
     int cl_status, cl_breakpoints;
     long long cl_rounds;
+    double phi_a, phi_b;       // the two terms of phi' = dot(s_c,Hd) + dot(g,d) (the guard band is relative to |a| + |b|)
 };
 
 // ---- block-wide deterministic reductions (fixed tree => run-to-run bit-identical) --------------------

@@ -550,6 +550,93 @@ int cauchy_step(S* h, double delta) {
     return BNL_OK;
 }
 
+// ---- cauchy_step :574-639 for the general projection (m_lin > 0), breakpoints evaluated on the Gram matrix, GUARDED --------
+// Whenever the trust region is active the reference's search walks up to n faces of the box, one Hd = H*d (:633) and one factor
+// update each.  Here the first kGramSwitch breakpoints of a search are the reference's own; if the search is still advancing,
+// G = J'J is formed ONCE per Jacobian on the FP64 tensor cores (gram.cu) and the following breakpoints take Hd from G (an
+// L2-resident n x n gemv instead of a pass over J).  G*d rounds differently from J'(Jd), so -- exactly like the device loop of the
+// bound-only case (cauchy_loop.cu) -- such a value only ever takes a decision that is outside a rounding band; an interior
+// minimiser (whose step length enters the iterate) and every in-band decision are re-evaluated with the literal Hd.  The Cauchy
+// point is therefore bit-identical to the literal search's, whatever the Gram matrix's own rounding (or reduction order across
+// GPUs) is.
+int cauchy_step_gram_guarded(S* h, double delta) {
+    constexpr int kGramSwitch = 8;
+    VecCtx& c = h->vc;
+    vk_active_reset(c, c.x, nullptr, h->stream);  // :591
+    KLAUNCH();
+    RET(rebuild_chol(h));
+    vk_cauchy_init(c, h->mask, h->stream);  // s_c = 0 ; d = P(-g) :592
+    KLAUNCH();
+    if (!h->mask) RET(project_general(h, c.g, c.d, true));
+    RET(hess_mul(h, c.d, c.hv));  // :609 (literal)
+    vk_cauchy_eval(c, delta, h->stream);
+    KLAUNCH();
+    RET(sync(h));
+    RET(check_chol(h));
+    bool literal = true;  // are the scalars in sh the literal ones?
+    int nbp = 0;
+    const int nmm = h->n - h->m_lin;
+    auto literal_eval = [&]() -> int {
+        RET(hess_mul(h, c.d, c.hv));
+        vk_cauchy_eval(c, delta, h->stream);
+        KLAUNCH();
+        RET(sync(h));
+        h->st.cauchy_literal_evals++;
+        literal = true;
+        return BNL_OK;
+    };
+    bool min_found = false;
+    while (!min_found && h->sh->nb_fix < nmm) {  // :615
+        if (!literal) {
+            // guard: may this Gram-derived (phi', phi'') take the decision "advance" on its own?
+            const double phi_p = h->sh->phi_p, phi_pp = h->sh->phi_pp, theta = h->sh->theta;
+            const double scale = std::fabs(h->sh->phi_a) + std::fabs(h->sh->phi_b);
+            bool clear_advance = false;
+            if (std::fabs(phi_p) > h->gram_guard * scale && phi_p < 0.0 && phi_pp > 0.0) {
+                const double relb = h->gram_guard * scale / std::fabs(phi_p) + h->gram_guard;
+                clear_advance = (-phi_p / phi_pp) > theta * (1.0 + relb);
+            }
+            if (!clear_advance) RET(literal_eval());  // stop, interior minimiser, or inside the band: the reference's own numbers decide
+        }
+        const double phi_p = h->sh->phi_p, phi_pp = h->sh->phi_pp, theta = h->sh->theta;
+        const double delta_t = (phi_pp > 0) ? -phi_p / phi_pp : 0.0;  // :618
+        if (literal && phi_p >= 0) {
+            min_found = true;
+        } else if (literal && phi_p < 0 && phi_pp > 0 && delta_t < theta) {
+            vk_cauchy_advance(c, h->mask, 0, h->stream);  // :625, literal step length
+            KLAUNCH();
+            min_found = true;
+        } else {
+            if (h->sh->bp_ind < 0) return h->fail(BNL_EBOUNDS, "BoundsError: next_breakpoint found no breakpoint (ind = -1)");
+            vk_cauchy_advance(c, h->mask, 1, h->stream);  // :628-632
+            KLAUNCH();
+            RET(downdate_chol(h));
+            if (!h->mask) RET(project_general(h, c.g, c.d, true));
+            ++nbp;
+            h->st.breakpoints++;
+            if (nbp >= kGramSwitch || h->gram_valid) {
+                if (!h->gram_valid) RET(form_gram(h));
+                CK(gram_apply(h->gram, h->n, h->ld, c.d, c.hv, h->stream));
+                h->st.kernel_launches += 2;
+                if (h->p > 0) {
+                    vk_hess_c(h->vc, c.d, c.hv, true, h->stream);
+                    KLAUNCH();
+                }
+                h->st.gram_breakpoints++;
+                literal = false;
+            } else {
+                RET(hess_mul(h, c.d, c.hv));  // :633 (literal)
+                literal = true;
+            }
+            vk_cauchy_eval(c, delta, h->stream);
+            KLAUNCH();
+            RET(sync(h));
+            RET(check_chol(h));
+        }
+    }
+    return BNL_OK;
+}
+
 // reduced-gradient norms of g and g_minor with the current active set (:420-421, :446-447)
 int nrg_general(S* h) {
     VecCtx& c = h->vc;
@@ -621,6 +708,8 @@ int inner_step(S* h, double delta, double* pred_out) {
     if (h->cauchy_mode == BNL_CAUCHY_INCREMENTAL && h->mask && h->p <= kCLMaxP && h->hess_mode == BNL_HESSIAN_MATRIX_FREE &&
         (h->nranks == 1 || h->p2p_on))
         RET(cauchy_step_incremental(h, delta));
+    else if (h->cauchy_mode == BNL_CAUCHY_INCREMENTAL && !h->mask && h->hess_mode == BNL_HESSIAN_MATRIX_FREE)
+        RET(cauchy_step_gram_guarded(h, delta));  // general projection: long searches take Hd from the Gram matrix, guarded
     else
         RET(cauchy_step(h, delta));  // :410
     RET(hess_mul(h, c.s, c.hv));      // g_minor = H*s+g :412

@@ -74,6 +74,8 @@ __global__ void k_cauchy_eval(VecCtx c, double delta) {
     block_argmin(th, ind, shd, shl);
     if (threadIdx.x == 0) {
         c.sd->phi_p = a + b;
+        c.sd->phi_a = a;
+        c.sd->phi_b = b;
         c.sd->phi_pp = e;
         c.sd->theta = th;
         c.sd->bp_ind = ind;

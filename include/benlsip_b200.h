@@ -92,6 +92,7 @@ typedef struct bnl_stats {
     int64_t chol_downdates;       /* O(m^2) rank-one downdates of the projection factor (one per Cauchy breakpoint, m_lin > 0) */
     double chol_ms;               /* CUDA-event time of the factor rebuilds + downdates                                */
     int64_t fused_jtr;            /* Jacobian generations that produced J'r on the fly (no J'w pass for the gradient)  */
+    int64_t gram_breakpoints;     /* Cauchy breakpoints (m_lin > 0) whose Hd came from the Gram matrix (guarded)        */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */
@@ -113,7 +114,10 @@ enum { BNL_HESSIAN_MATRIX_FREE = 0, BNL_HESSIAN_GRAM = 1 };
  * t = J d and u = J s_c are updated in place (one strided column of J + two M-vector streams) by ONE persistent device
  * kernel that walks the breakpoints without host round trips.  The loop is guarded: a decision inside a rounding band, and
  * every interior minimiser (whose step length enters the iterate), is re-evaluated with the literal Hd = H*d, so the Cauchy
- * point is bit-identical to the literal search's.  Environment: BNL_CAUCHY=literal selects LITERAL at bnl_create.           */
+ * point is bit-identical to the literal search's.  With linear equality constraints (m_lin > 0) the same guard is applied to
+ * breakpoints evaluated on G = J'J (formed once per Jacobian on the FP64 tensor cores when a search walks more than 8
+ * breakpoints): again every number that reaches the iterate is literal.  Environment: BNL_CAUCHY=literal selects LITERAL at
+ * bnl_create; BNL_CAUCHY_GUARD / BNL_GRAM_GUARD set the relative widths of the rounding bands (1e-9 / 1e-7).                */
 enum { BNL_CAUCHY_LITERAL = 0, BNL_CAUCHY_INCREMENTAL = 1 };
 
 /* Built-in device-side models (definitions in oracle/models.py, the executable spec). */

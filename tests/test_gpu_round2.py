@@ -297,3 +297,30 @@ def test_cfg4_family_mid_size_against_golden(S):
     F = assert_trajectory_parity("mixed_4000_64_8", tr, x, tail_outer=1, tail_inner=50, tail_x=1e-10)
     assert F is None or F >= 50
     assert abs(P.nlconstraints(x)[0]) < 1e-8 and np.max(np.abs(P.A @ x - P.b)) < 1e-12
+
+
+def test_gram_guarded_cauchy_search_equals_literal_search_with_linear_constraints():
+    """m_lin > 0 (general projection): long Cauchy searches take Hd from G = J'J after their 8th breakpoint, guarded exactly like
+    the bound-only device loop -- the whole AL solve (x, y, mu, active set, every count) must be bit-identical to the literal search
+    (BNL_CAUCHY_LITERAL: one pass over J per breakpoint), with most breakpoints served by the Gram matrix."""
+    P = MixedConstraintProblem(600, 24, 4)
+    kw = dict(max_outer_iter=60, max_inner_iter=200)
+    res = []
+    for mode in (B.CAUCHY_INCREMENTAL, B.CAUCHY_LITERAL):
+        T = B.Solver(0)
+        T.set_problem(P.M, P.n, P.A, P.xlow, P.xupp, p=1)
+        T.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, P.seed)
+        T.model_set_truth(P.x_star, P.x0)
+        T.use_builtin_nlcons(B.NLCONS_SPHERE, P.rho2)
+        T.set_cauchy_mode(mode)
+        tr = {}
+        x, y = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=T, trace=tr, **kw)
+        res.append((x, y, tr))
+        T.close()
+    (xg, yg, tg), (xl, yl, tl) = res
+    sg, sl = tg["stats"], tl["stats"]
+    assert np.array_equal(xg, xl) and np.array_equal(yg, yl) and tg["mu"] == tl["mu"]
+    assert np.array_equal(tg["fixvars_words"], tl["fixvars_words"])
+    assert (tg["outer_iters"], sg["inner_iters"], sg["minor_iters"], sg["cg_iters"], sg["breakpoints"]) == \
+           (tl["outer_iters"], sl["inner_iters"], sl["minor_iters"], sl["cg_iters"], sl["breakpoints"])
+    assert sg["gram_breakpoints"] > 0 and sl["gram_breakpoints"] == 0 and sg["j_passes"] < sl["j_passes"]
