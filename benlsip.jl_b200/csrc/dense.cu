@@ -241,16 +241,16 @@ __global__ void k_rs_rebuild(DenseCtx c, const unsigned char* fix) {
 // One variable left the free set (add_active!(ind), src/polyhedral_constraints.jl:240-249): A_free A_free' loses the rank-one
 // term a a' with a = A[:,ind], so its Cholesky factor is DOWNDATED in O(m^2) (hyperbolic rotations, LINPACK dchdd) instead of
 // being rebuilt from the O(m^2 n) products -- the reference rebuilds its (m+q)^2 factor from scratch here and flags the cost
-// itself (:51).  One warp; `ind` is read from the device scalars of the scan that chose the breakpoint.
-__global__ void k_rs_downdate(DenseCtx c) {
-    const int m = c.m, lane = threadIdx.x;
-    const long long ind = c.sd->bp_ind;
-    double* a = c.ywork;  // m-vector workspace
-    if (ind >= 0) {
-        for (int i = lane; i < m; i += 32) a[i] = c.A[(size_t)i * c.ld + ind];
-        __syncwarp();
+// itself (:51).  Executed by warp 0 of the CTA on a shared-memory copy of the factor (sL: m*m doubles, sa: m doubles).
+__device__ void rs_downdate_dev(const DenseCtx& c, long long ind, double* sL, double* sa) {
+    const int m = c.m;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) sL[e] = c.Lr[e];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) sa[i] = c.A[(size_t)i * c.ld + ind];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         for (int k = 0; k < m; ++k) {
-            const double lkk = c.Lr[(size_t)k * m + k], ak = a[k];
+            const double lkk = sL[(size_t)k * m + k], ak = sa[k];
             const double r2 = lkk * lkk - ak * ak;
             if (!(r2 > 0.0)) {  // A_free lost full row rank: PosDefException in the reference (:57)
                 if (lane == 0) c.sd->chol_fail = 1;
@@ -258,28 +258,41 @@ __global__ void k_rs_downdate(DenseCtx c) {
             }
             const double r = sqrt(r2), cc = r / lkk, ss = ak / lkk;
             __syncwarp();
-            if (lane == 0) c.Lr[(size_t)k * m + k] = r;
+            if (lane == 0) sL[(size_t)k * m + k] = r;
             for (int i = k + 1 + lane; i < m; i += 32) {
-                const double lik = (c.Lr[(size_t)k * m + i] - ss * a[i]) / cc;
-                c.Lr[(size_t)k * m + i] = lik;
-                a[i] = cc * a[i] - ss * lik;
+                const double lik = (sL[(size_t)k * m + i] - ss * sa[i]) / cc;
+                sL[(size_t)k * m + i] = lik;
+                sa[i] = cc * sa[i] - ss * lik;
             }
             __syncwarp();
         }
     }
-    __syncwarp();
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) c.Lr[e] = sL[e];
+    __syncthreads();
+}
+
+__device__ void publish_scal(const DenseCtx& c) {
+    __syncthreads();
     const int nwords = sizeof(Scal) / 8;
     const unsigned long long* s = reinterpret_cast<const unsigned long long*>(c.sd);
     unsigned long long* d = reinterpret_cast<unsigned long long*>(c.sh);
-    for (int i = lane; i < nwords; i += 32) d[i] = s[i];
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) d[i] = s[i];
 }
 
-__global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double* r, double* v, int negate) {
+__global__ void k_rs_downdate(DenseCtx c) {
+    extern __shared__ double dsm[];
+    const long long ind = c.sd->bp_ind;
+    if (ind >= 0) rs_downdate_dev(c, ind, dsm, dsm + (size_t)c.m * c.m);
+    publish_scal(c);
+}
+
+// v = P(+-r) in the reduced space (whole CTA): t = A_free r_free ; Lr y = t ; Lr' w = y ; v_free = r_free - A_free' w ; v_F = 0
+__device__ void rs_project_dev(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, int negate) {
     const int m = c.m;
     const double sgn = negate ? -1.0 : 1.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     double* y = c.ywork;
-    // t = A_free r_free
     for (int i = warp; i < m; i += nw) {
         double s = 0.0;
         for (int j = lane; j < c.n; j += 32)
@@ -307,7 +320,6 @@ __global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double*
         }
     }
     __syncthreads();
-    // v_free = r_free - A_free' w ; v_F = 0
     for (int j = threadIdx.x; j < c.n; j += blockDim.x) {
         double out = 0.0;
         if (!fix[j]) {
@@ -319,12 +331,114 @@ __global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double*
     }
 }
 
+__global__ void k_rs_project(DenseCtx c, const unsigned char* fix, const double* r, double* v, int negate) {
+    rs_project_dev(c, fix, r, v, negate);
+}
+
+// One Cauchy breakpoint of the general path in ONE launch (src/basic_tralcnlss.jl:628-632): s_c += theta d ; add_active!(ind)
+// (flag + factor downdate) ; d = P(-g).  Same arithmetic, in the same order, as k_cauchy_advance<false> + k_rs_downdate +
+// k_rs_project launched one after the other; the factor stays in shared memory between the downdate and the two triangular
+// solves of the projection.
+__global__ void k_rs_breakpoint(DenseCtx c, double* s, double* d, const double* g, unsigned char* fix) {
+    extern __shared__ double dsm[];
+    const int m = c.m;
+    double* sL = dsm;                      // m x m factor
+    double* sa = dsm + (size_t)m * m;      // m: the leaving column, then the projection's m-vector
+    const double step = c.sd->theta;
+    const long long ind = c.sd->bp_ind;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
+        s[i] = s[i] + step * d[i];
+        if (i == ind) fix[i] = 1;
+    }
+    if (threadIdx.x == 0) c.sd->nb_fix = c.sd->nb_fix + 1;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) sL[e] = c.Lr[e];
+    if (ind >= 0)
+        for (int i = threadIdx.x; i < m; i += blockDim.x) sa[i] = c.A[(size_t)i * c.ld + ind];
+    __syncthreads();
+    if (ind >= 0 && warp == 0) {  // downdate (rs_downdate_dev's arithmetic)
+        for (int k = 0; k < m; ++k) {
+            const double lkk = sL[(size_t)k * m + k], ak = sa[k];
+            const double r2 = lkk * lkk - ak * ak;
+            if (!(r2 > 0.0)) {
+                if (lane == 0) c.sd->chol_fail = 1;
+                break;
+            }
+            const double r = sqrt(r2), cc = r / lkk, ss = ak / lkk;
+            __syncwarp();
+            if (lane == 0) sL[(size_t)k * m + k] = r;
+            for (int i = k + 1 + lane; i < m; i += 32) {
+                const double lik = (sL[(size_t)k * m + i] - ss * sa[i]) / cc;
+                sL[(size_t)k * m + i] = lik;
+                sa[i] = cc * sa[i] - ss * lik;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) c.Lr[e] = sL[e];
+    // d = P(-g) (rs_project_dev's arithmetic with negate = 1, factor and m-vector in shared memory)
+    double* y = sa;
+    for (int i = warp; i < m; i += nw) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int j = lane; j < c.n; j += 32)
+            if (!fix[j]) t = fma(__ldg(c.A + (size_t)i * c.ld + j), -1.0 * g[j], t);
+        t = warp_sum(t);
+        if (lane == 0) y[i] = t;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int k = 0; k < m; ++k) {
+            const double yk = y[k] / sL[(size_t)k * m + k];
+            __syncwarp();
+            if (lane == 0) y[k] = yk;
+            for (int i = k + 1 + lane; i < m; i += 32) y[i] -= sL[(size_t)k * m + i] * yk;
+            __syncwarp();
+        }
+        for (int k = m - 1; k >= 0; --k) {
+            double t = 0.0;
+            for (int i = k + 1 + lane; i < m; i += 32) t = fma(sL[(size_t)k * m + i], y[i], t);
+            t = warp_sum(t);
+            __syncwarp();
+            if (lane == 0) y[k] = (y[k] - t) / sL[(size_t)k * m + k];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < c.n; j += blockDim.x) {
+        double out = 0.0;
+        if (!fix[j]) {
+            double t = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < m; ++i) t = fma(__ldg(c.A + (size_t)i * c.ld + j), y[i], t);
+            out = -1.0 * g[j] - t;
+        }
+        d[j] = out;
+    }
+    publish_scal(c);
+}
+
 }  // namespace
 
 void dk_left_mul(const DenseCtx& c, const double* x, double* y, cudaStream_t st) { k_left_mul<<<1, kDT, 0, st>>>(c, x, y); }
 void dk_left_mul_tr(const DenseCtx& c, const double* y, double* x, cudaStream_t st) { k_left_mul_tr<<<1, kDT, 0, st>>>(c, y, x); }
 void dk_rs_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st) { k_rs_rebuild<<<1, kDT, 0, st>>>(c, fix); }
-void dk_rs_downdate(const DenseCtx& c, cudaStream_t st) { k_rs_downdate<<<1, 32, 0, st>>>(c); }
+static size_t rs_smem(const DenseCtx& c) { return ((size_t)c.m * c.m + c.m) * sizeof(double); }
+bool dk_rs_downdate_fits(const DenseCtx& c) {  // the factor must fit in shared memory (m <= 160); above: rebuild instead
+    static bool opted = false;
+    if (rs_smem(c) <= 48 * 1024) return true;
+    if (rs_smem(c) > 200 * 1024) return false;
+    if (!opted) {
+        opted = cudaFuncSetAttribute(k_rs_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+                cudaFuncSetAttribute(k_rs_breakpoint, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+    }
+    return opted;
+}
+void dk_rs_downdate(const DenseCtx& c, cudaStream_t st) { k_rs_downdate<<<1, 256, rs_smem(c), st>>>(c); }
+void dk_rs_breakpoint(const DenseCtx& c, double* s, double* d, const double* g, unsigned char* fix, cudaStream_t st) {
+    k_rs_breakpoint<<<1, kDT, rs_smem(c), st>>>(c, s, d, g, fix);
+}
 void dk_rs_project(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, bool negate, cudaStream_t st) {
     k_rs_project<<<1, kDT, 0, st>>>(c, fix, r, v, negate ? 1 : 0);
 }

@@ -38,7 +38,10 @@ void dk_left_mul_tr(const DenseCtx& c, const double* y, double* x, cudaStream_t 
 // condition (A_free rank deficient <=> PosDefException), different rounding.
 void dk_rs_rebuild(const DenseCtx& c, const unsigned char* fix, cudaStream_t st);
 // the variable sd->bp_ind just left the free set: rank-one downdate of the m x m factor, O(m^2)
+bool dk_rs_downdate_fits(const DenseCtx& c);  // the m x m factor fits in shared memory (m <= 160)
 void dk_rs_downdate(const DenseCtx& c, cudaStream_t st);
+// one Cauchy breakpoint in one launch: s += theta d ; fix[ind] = 1 ; downdate ; d = P(-g)   (theta, ind from the device scalars)
+void dk_rs_breakpoint(const DenseCtx& c, double* s, double* d, const double* g, unsigned char* fix, cudaStream_t st);
 void dk_rs_project(const DenseCtx& c, const unsigned char* fix, const double* r, double* v, bool negate, cudaStream_t st);
 
 }  // namespace bnl

@@ -201,6 +201,11 @@ cudaError_t gram_apply(const double* G, int n, int ld, const double* v, double* 
     return cudaGetLastError();
 }
 
+cudaError_t gram_gemv(const double* G, int n, int ld, const double* v, double* y, cudaStream_t st) {
+    gram_gemv_kernel<<<(n + 7) / 8, 256, 0, st>>>(G, n, ld, v, y);
+    return cudaGetLastError();
+}
+
 double gram_flops(long long M, int ld) {
     const int ntile = (ld + TB - 1) / TB;
     const double npairs = ntile * (ntile + 1) / 2.0;

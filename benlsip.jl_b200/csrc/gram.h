@@ -9,5 +9,6 @@ cudaError_t gram_launch(const double* J, long long M, int ld, double* G, double*
 int gram_pick_split(long long M, int ld, int sm_count);
 // y[0..n) = G v ; y[ld] = v'Gv
 cudaError_t gram_apply(const double* G, int n, int ld, const double* v, double* y, cudaStream_t st);
+cudaError_t gram_gemv(const double* G, int n, int ld, const double* v, double* y, cudaStream_t st);  // y[0..n) = G v only
 double gram_flops(long long M, int ld);
 }  // namespace bnl

@@ -227,7 +227,7 @@ int rebuild_chol(S* h) {  // update_chol! :62-68 (general path only; for m_lin =
 // (the literal block factor, BNL_LITERAL_PROJECTION=1, is rebuilt as in the reference)
 int downdate_chol(S* h) {
     if (h->mask) return BNL_OK;
-    if (h->literal_proj) return rebuild_chol(h);
+    if (h->literal_proj || !dk_rs_downdate_fits(h->dc)) return rebuild_chol(h);
     EvScope ev(h, 6);
     dk_rs_downdate(h->dc, h->stream);
     KLAUNCH();
@@ -608,16 +608,24 @@ int cauchy_step_gram_guarded(S* h, double delta) {
             min_found = true;
         } else {
             if (h->sh->bp_ind < 0) return h->fail(BNL_EBOUNDS, "BoundsError: next_breakpoint found no breakpoint (ind = -1)");
-            vk_cauchy_advance(c, h->mask, 1, h->stream);  // :628-632
-            KLAUNCH();
-            RET(downdate_chol(h));
-            if (!h->mask) RET(project_general(h, c.g, c.d, true));
+            if (!h->literal_proj && dk_rs_downdate_fits(h->dc)) {
+                // :628-632 in one launch: s_c += theta d ; add_active!(ind) (flag + O(m^2) factor downdate) ; d = P(-g)
+                EvScope ev(h, 6);
+                dk_rs_breakpoint(h->dc, c.s, c.d, c.g, c.fix, h->stream);
+                KLAUNCH();
+                h->st.chol_downdates++;
+            } else {
+                vk_cauchy_advance(c, h->mask, 1, h->stream);
+                KLAUNCH();
+                RET(downdate_chol(h));
+                RET(project_general(h, c.g, c.d, true));
+            }
             ++nbp;
             h->st.breakpoints++;
             if (nbp >= kGramSwitch || h->gram_valid) {
                 if (!h->gram_valid) RET(form_gram(h));
-                CK(gram_apply(h->gram, h->n, h->ld, c.d, c.hv, h->stream));
-                h->st.kernel_launches += 2;
+                CK(gram_gemv(h->gram, h->n, h->ld, c.d, c.hv, h->stream));  // Hd ~ G d  (k_cauchy_eval takes the dots itself)
+                KLAUNCH();
                 if (h->p > 0) {
                     vk_hess_c(h->vc, c.d, c.hv, true, h->stream);
                     KLAUNCH();
@@ -831,6 +839,7 @@ int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double o
                 return buf;
             };
             fprintf(log, "%4d   %s   %s   %s   %s\n", k, e(6, mx).c_str(), e(2, rec.norm_s).c_str(), e(2, delta).c_str(), e(2, rho).c_str());
+            fflush(log);  // a long solve can be followed (and a cut-off one read) from its log
         }
         if (rho > h->prm.eta1) {  // :358-363
             CK(cudaMemcpyAsync(c.x, c.xn, (size_t)h->ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
