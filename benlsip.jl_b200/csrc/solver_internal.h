@@ -106,7 +106,6 @@ struct bnl_solver {
     unsigned int* cl_sync = nullptr;             // arrive counter + broadcast record of the persistent loop kernel
     double cauchy_guard = 1e-9;                  // relative width of the loop's rounding band
     double gram_guard = 1e-7;                    // the same for breakpoints evaluated on the Gram matrix (general projection)
-    bool hv_holds_Hs = false;                    // hv = H*s of the CURRENT s (its slot [ld] = ||J s||^2): vthv(s) is free
 
     // model binding
     int model_id = 0;
