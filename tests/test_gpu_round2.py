@@ -275,16 +275,17 @@ def test_fused_jacobian_gradient_is_bit_identical(M, n):
     assert np.array_equal(a[7], b[7])
 
 
-def test_cfg4_family_mid_size_against_golden(S):
-    """cfg4 family (linear equalities + sphere constraint + box) at M = 4000, n = 64, m_lin = 8 through the device path: 684
-    inner iterations, ~32 000 Cauchy breakpoints -- each one a rank-one DOWNDATE of the projection factor (csrc/dense.cu) where
-    the reference rebuilds its (m+q)^2 factor (src/polyhedral_constraints.jl:62-68) -- mu from 10 to 1e11.  Against the oracle's
-    golden (which uses the literal block factor): exact per-iteration comparison of the first 57 inner iterations; from there
-    on the trust-region radius is of the order of the active-set tolerance sqrt(eps), so which faces count as active is decided
-    by the last bits of s (tests/parity.py) and the end state is compared: same outer / inner counts, final x to 1e-10 (measured
-    1e-13)."""
+@pytest.mark.parametrize("name", ["mixed_4000_64_8", "mixed_20000_256_16"])
+def test_cfg4_family_mid_size_against_golden(S, name):
+    """cfg4 family (linear equalities + sphere constraint + box) at mid sizes through the device path -- (M, n, m_lin) =
+    (4000, 64, 8): 684 inner iterations, ~32 000 Cauchy breakpoints; (20 000, 256, 16): 503 inner iterations, ~100 000 breakpoints
+    (the oracle needs 1 h 55 min of CPU for it) -- each breakpoint a rank-one DOWNDATE of the projection factor (csrc/dense.cu)
+    where the reference rebuilds its (m+q)^2 factor (src/polyhedral_constraints.jl:62-68), most of them evaluated on the Gram
+    matrix under the guard; mu from 10 to 1e11.  Against the oracle's golden (literal block factor, literal search): exact
+    per-iteration comparison up to the golden's first fragile record (here: the trust-region radius reaches the order of the
+    active-set tolerance sqrt(eps), tests/parity.py), then the end state: same outer count, final x to 1e-9."""
     from tests.parity import assert_trajectory_parity, golden
-    g = golden("mixed_4000_64_8")
+    g = golden(name)
     P = MixedConstraintProblem(g["M"], g["n"], g["m_lin"])
     S.set_problem(P.M, P.n, P.A, P.xlow, P.xupp, p=1)
     S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, P.seed)
@@ -293,10 +294,10 @@ def test_cfg4_family_mid_size_against_golden(S):
     tr = {}
     x, y = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=S, trace=tr, max_outer_iter=60, max_inner_iter=200)
     st = tr["stats"]
-    assert st["chol_downdates"] == st["breakpoints"] > 10_000
-    F = assert_trajectory_parity("mixed_4000_64_8", tr, x, tail_outer=1, tail_inner=50, tail_x=1e-10)
-    assert F is None or F >= 50
-    assert abs(P.nlconstraints(x)[0]) < 1e-8 and np.max(np.abs(P.A @ x - P.b)) < 1e-12
+    assert st["chol_downdates"] == st["breakpoints"] > 10_000 and st["gram_breakpoints"] > 0.5 * st["breakpoints"]
+    F = assert_trajectory_parity(name, tr, x, tail_outer=1, tail_inner=60, tail_x=1e-9)
+    assert F is None or F >= 40
+    assert abs(P.nlconstraints(x)[0]) < 1e-8 and np.max(np.abs(P.A @ x - P.b)) < 1e-11
 
 
 def test_gram_guarded_cauchy_search_equals_literal_search_with_linear_constraints():
