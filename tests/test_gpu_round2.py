@@ -325,3 +325,33 @@ def test_gram_guarded_cauchy_search_equals_literal_search_with_linear_constraint
     assert (tg["outer_iters"], sg["inner_iters"], sg["minor_iters"], sg["cg_iters"], sg["breakpoints"]) == \
            (tl["outer_iters"], sl["inner_iters"], sl["minor_iters"], sl["cg_iters"], sl["breakpoints"])
     assert sg["gram_breakpoints"] > 0 and sl["gram_breakpoints"] == 0 and sg["j_passes"] < sl["j_passes"]
+
+
+@pytest.mark.parametrize("M,n", [(3000, 96), (2000, 1000), (5000, 330)])
+def test_device_cauchy_loop_randomized_equals_literal(S, M, n):
+    """The guarded device loop against the literal search on random states: iterates scattered in the box (some components on
+    their bounds), radii from 1e-9 to 1e3 (no breakpoint / a few / nearly all variables on trust-region faces).  inner_step's
+    step, predicted reduction and active set must be bit-identical in every case."""
+    P = GlmProblem(M, n, seed=3)
+    S.set_problem(M, n)
+    S.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+    rng = np.random.default_rng(M + n)
+    nbp = 0
+    for case in range(12):
+        x = np.clip(rng.normal(0.0, 0.7, n), -1.0, 1.0)
+        x[rng.random(n) < 0.1] = 1.0
+        x[rng.random(n) < 0.1] = -1.0
+        delta = float(10.0 ** rng.uniform(-9, 3))
+        mx, g, _ = S.new_point(x, None, 10.0)
+        out = []
+        for mode in (B.CAUCHY_LITERAL, B.CAUCHY_INCREMENTAL):
+            S.set_cauchy_mode(mode)
+            S.reset_stats()
+            s, pred = S.inner_step(x, g, delta)
+            out.append((s, pred, S.fixvars_words(), S.stats()))
+        (sl, pl, wl, stl), (si, pi, wi, sti) = out
+        assert np.array_equal(si, sl) and pi == pl and np.array_equal(wi, wl), (case, delta)
+        assert sti["breakpoints"] == stl["breakpoints"] and sti["cg_iters"] == stl["cg_iters"]
+        nbp += sti["breakpoints"]
+    assert nbp > n  # the cases did walk breakpoints
+    S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
