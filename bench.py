@@ -49,6 +49,9 @@ CFG = {
     # src/basic_tralcnlss.jl:690-764) carry the solve
     "cfg3cg": dict(M=10_000_000, n=1024, model="glm", seed=3, noise=1e-3, cond_exp=1.0, interior_truth=True),
     "cfg2": dict(M=1_000_000, n=256, model="expsum", seed=1, noise=1e-3, cond_exp=0.0),
+    # BASELINE config[1] as SURVEY 8d words it: ONE 128-term exponential sum on one time grid (kappa(J) ~ 1e16: the reference
+    # algorithm exhausts max_inner_iter on it, so it is run with --max-outer / --max-inner caps)
+    "cfg2dense": dict(M=1_000_000, n=256, model="expsum_dense", seed=1, noise=1e-3, cond_exp=0.0),
     # BASELINE config[4]: ill-conditioned (column scaling 10^(-6 j/n)), J = 327.7 GB: needs >= 2 GPUs, quoted at 8; the reference
     # algorithm does not reach its tolerance on it, so it is run with iteration caps (--max-outer / --max-inner)
     "cfg5": dict(M=10_000_000, n=4096, model="glm", seed=3, noise=1e-3, cond_exp=6.0),
@@ -114,9 +117,11 @@ def host_threads():
 
 
 def oracle_problem(cfg, M_s):
-    from oracle.models import ExpSumProblem, GlmProblem
+    from oracle.models import DenseExpSumProblem, ExpSumProblem, GlmProblem
 
     n = cfg["n"]
+    if cfg["model"] == "expsum_dense":
+        return DenseExpSumProblem(M_s, n, seed=cfg["seed"])
     if cfg["model"] == "glm":
         P = GlmProblem(M_s, n, seed=cfg["seed"], noise=cfg["noise"], cond_exp=cfg["cond_exp"])
         if cfg.get("interior_truth"):
@@ -213,7 +218,8 @@ def make_solver(B, cfg, args, local_rank, world, rank, M):
         solve_kw = dict(max_outer_iter=args.max_outer or 500, max_inner_iter=args.max_inner or 500)
     else:
         S.set_problem(M_loc, n, M_total=M, row0=row0)
-        S.use_builtin_model(B.MODEL_GLM if cfg["model"] == "glm" else B.MODEL_EXPSUM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
+        S.use_builtin_model({"glm": B.MODEL_GLM, "expsum": B.MODEL_EXPSUM, "expsum_dense": B.MODEL_EXPSUM_DENSE}[cfg["model"]],
+                            cfg["noise"], cfg["cond_exp"], cfg["seed"])
         if cfg.get("interior_truth"):
             S.model_set_truth(interior_truth(n, cfg["seed"]))
         if args.max_outer:
@@ -408,7 +414,8 @@ def cpu_baseline(args, cfg, B, local_rank):
     try:
         T = B.Solver(local_rank)
         T.set_problem(M_s, cfg["n"])
-        T.use_builtin_model(B.MODEL_GLM if cfg["model"] == "glm" else B.MODEL_EXPSUM, cfg["noise"], cfg["cond_exp"], cfg["seed"])
+        T.use_builtin_model({"glm": B.MODEL_GLM, "expsum": B.MODEL_EXPSUM, "expsum_dense": B.MODEL_EXPSUM_DENSE}[cfg["model"]],
+                            cfg["noise"], cfg["cond_exp"], cfg["seed"])
         if cfg.get("interior_truth"):
             T.model_set_truth(interior_truth(cfg["n"], cfg["seed"]))
         x0 = T.model_vectors()["x0"]

@@ -26,7 +26,7 @@ SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)
 
 # CG_status (src/basic_tralcnlss.jl:12); NOTHING is Julia's `nothing` (trap T3)
 CG_SOLVED, CG_BOUND_HIT, CG_NEGATIVE_CURVATURE, CG_MAX_ITER, CG_NOTHING = 0, 1, 2, 3, -1
-MODEL_GLM, MODEL_EXPSUM = 1, 2
+MODEL_GLM, MODEL_EXPSUM, MODEL_EXPSUM_DENSE = 1, 2, 3
 HESSIAN_MATRIX_FREE, HESSIAN_GRAM = 0, 1
 NLCONS_SPHERE = 1
 CAUCHY_LITERAL, CAUCHY_INCREMENTAL = 0, 1

@@ -424,6 +424,26 @@ int bnl_use_builtin_model(bnl_handle h, int32_t model_id, const double* params, 
             }
             h->m_x0[j] = 0.5 * (h->m_xlow[j] + h->m_xupp[j]);
         }
+    } else if (model_id == BNL_MODEL_EXPSUM_DENSE) {
+        // oracle/models.py: DenseExpSumProblem (one K-term exponential sum on one time grid, SURVEY 8d cfg2 as worded)
+        if (n % 2) return h->fail(BNL_EDIM, "EXPSUM_DENSE needs an even n");
+        if (n > 4096) return h->fail(BNL_EDIM, "EXPSUM_DENSE supports n <= 4096");
+        const int K = n / 2;
+        for (int k = 0; k < K; ++k) {
+            h->m_xtrue[k] = 1.0 + u01(hash_rc(rowkey(seed, 0ull), (uint32_t)k));
+            h->m_xtrue[K + k] = 0.5 * (double)k + u01(hash_rc(rowkey(seed, 1ull), (uint32_t)k));
+        }
+        for (int j = 0; j < n; ++j) {
+            const double xt = h->m_xtrue[j];
+            if (j % 8 == 0) {
+                h->m_xlow[j] = xt;
+                h->m_xupp[j] = xt + 0.5;
+            } else {
+                h->m_xlow[j] = xt - 0.25;
+                h->m_xupp[j] = xt + 0.25;
+            }
+            h->m_x0[j] = 0.5 * (h->m_xlow[j] + h->m_xupp[j]);
+        }
     } else {
         return h->fail(BNL_EINVAL, "unknown builtin model %d", model_id);
     }

@@ -224,6 +224,70 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) expsum_jac_kernel(ModelArgs
     }
 }
 
+// ---------------------------------------------------------------- EXPSUM_DENSE ---------------------------
+// BASELINE config[1] as SURVEY 8d words it: ONE sum of K = n/2 exponentials observed on one time grid,
+//   model_i(x) = sum_k a_k exp(-b_k t_i),  t_i = (i + 0.5) / M_total,  x = [a_0..a_{K-1}, b_0..b_{K-1}]
+//   J_{i,k} = exp(-b_k t_i),  J_{i,K+k} = -a_k t_i exp(-b_k t_i)      (a dense M x n Jacobian)
+template <int WHAT>
+__global__ void __launch_bounds__(256) expsum_dense_rows_kernel(ModelArgs a, const double* __restrict__ x, const double* __restrict__ yin,
+                                                                double* __restrict__ out, double* __restrict__ partial) {
+    extern __shared__ double2 sab[];  // [K] (a_k, b_k)
+    __shared__ double shd[32];
+    const int K = a.n / 2;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) sab[k] = make_double2(x[k], x[K + k]);
+    __syncthreads();
+    long long i0, i1, istep;
+    if (WHAT == 1) {  // one row chunk per CTA (rowgeom.h)
+        const int cg = blockIdx.x / a.geo.G, cb = blockIdx.x % a.geo.G;
+        i0 = a.geo.local_begin(cg, cb) + threadIdx.x;
+        i1 = a.geo.local_end(cg, cb);
+        istep = blockDim.x;
+    } else {
+        i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        i1 = a.M;
+        istep = (long long)gridDim.x * blockDim.x;
+    }
+    double ss = 0.0;
+    for (long long i = i0; i < i1; i += istep) {
+        const long long gi = a.row0 + i;
+        const double t = ((double)gi + 0.5) / (double)a.M_total;
+        double m = 0.0;
+        for (int k = 0; k < K; ++k) m = fma(sab[k].x, exp(-sab[k].y * t), m);
+        if (WHAT == 0) {
+            out[i] = m + a.noise * usym(hash_rc(rowkey(a.seed + 1u, (unsigned long long)gi), 0u));
+        } else {
+            const double r = m - yin[i];
+            out[i] = r;
+            ss = fma(r, r, ss);
+        }
+    }
+    if (WHAT == 1) {
+        ss = block_sum(ss, shd);
+        if (threadIdx.x == 0) partial[blockIdx.x] = ss;
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) expsum_dense_jac_kernel(ModelArgs a, const double* __restrict__ x,
+                                                                             double* __restrict__ J) {
+    const int K = a.n / 2;
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * kWarpsPerCta;
+    for (long long i = gw; i < a.M; i += nw) {
+        const long long gi = a.row0 + i;
+        const double t = ((double)gi + 0.5) / (double)a.M_total;
+        double* Jrow = J + (size_t)i * a.ld;
+        for (int j = lane; j < a.ld; j += 32) {
+            double v = 0.0;  // padding columns
+            if (j < K)
+                v = exp(-x[K + j] * t);
+            else if (j < a.n)
+                v = -(x[j - K] * t) * exp(-x[j] * t);
+            Jrow[j] = v;
+        }
+    }
+}
+
 int rows_grid(long long M, int nblocks_cap) {
     long long g = (M + kWarpsPerCta - 1) / kWarpsPerCta;
     if (g > nblocks_cap) g = nblocks_cap;
@@ -249,6 +313,8 @@ cudaError_t model_setup_y(const ModelArgs& a, const double* x_true, double* y, c
         glm_rows_kernel<0><<<rows_grid(a.M / 32 + 1, 148 * 8), 256, (size_t)a.ld * sizeof(double2), st>>>(a, x_true, nullptr, y, nullptr);
     } else if (a.model_id == 2) {
         expsum_rows_kernel<0><<<rows_grid(a.M / 32 + 1, 148 * 8), 256, 0, st>>>(a, x_true, nullptr, y, nullptr);
+    } else if (a.model_id == 3) {
+        expsum_dense_rows_kernel<0><<<rows_grid(a.M / 32 + 1, 148 * 8), 256, (size_t)(a.n / 2) * sizeof(double2), st>>>(a, x_true, nullptr, y, nullptr);
     } else {
         return cudaErrorInvalidValue;
     }
@@ -263,6 +329,8 @@ cudaError_t model_residual(const ModelArgs& a, const double* x, const double* y,
         glm_rows_kernel<1><<<grid, 256, (size_t)a.ld * sizeof(double2), st>>>(a, x, y, r, partial);
     } else if (a.model_id == 2) {
         expsum_rows_kernel<1><<<grid, 256, 0, st>>>(a, x, y, r, partial);
+    } else if (a.model_id == 3) {
+        expsum_dense_rows_kernel<1><<<grid, 256, (size_t)(a.n / 2) * sizeof(double2), st>>>(a, x, y, r, partial);
     } else {
         return cudaErrorInvalidValue;
     }
@@ -274,6 +342,8 @@ cudaError_t model_jacobian(const ModelArgs& a, const double* x, double* J, cudaS
         glm_jac_kernel<<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x, J);
     } else if (a.model_id == 2) {
         expsum_jac_kernel<<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x, J);
+    } else if (a.model_id == 3) {
+        expsum_dense_jac_kernel<<<rows_grid(a.M, 148 * 8), kWarpsPerCta * 32, 0, st>>>(a, x, J);
     } else {
         return cudaErrorInvalidValue;
     }

@@ -121,7 +121,7 @@ enum { BNL_HESSIAN_MATRIX_FREE = 0, BNL_HESSIAN_GRAM = 1 };
 enum { BNL_CAUCHY_LITERAL = 0, BNL_CAUCHY_INCREMENTAL = 1 };
 
 /* Built-in device-side models (definitions in oracle/models.py, the executable spec). */
-enum { BNL_MODEL_GLM = 1, BNL_MODEL_EXPSUM = 2 };
+enum { BNL_MODEL_GLM = 1, BNL_MODEL_EXPSUM = 2 /* n/2 channel-separated decays */, BNL_MODEL_EXPSUM_DENSE = 3 /* one n/2-term sum */ };
 /* Built-in nonlinear equality constraint (p = 1) for the device models: c(x) = x'x - rho2, params = {rho2}. */
 enum { BNL_NLCONS_SPHERE = 1 };
 

@@ -192,6 +192,48 @@ class ExpSumProblem(BoundProblem):
         return J
 
 
+class DenseExpSumProblem(BoundProblem):
+    """
+    cfg2 as SURVEY 8d words it (model id 3): ONE sum of K = n/2 exponentials observed on one time grid,
+        model_i(x) = sum_k a_k exp(-b_k t_i),   t_i = (i + 0.5) / M_total,   x = [a_0..a_{K-1}, b_0..b_{K-1}]
+        J_{i,k} = exp(-b_k t_i),  J_{i,K+k} = -a_k t_i exp(-b_k t_i)
+        x_true: a_k = 1 + unif(seed,0,k), b_k = 0.5 k + unif(seed,1,k);  y = model(x_true) + noise * sym(seed+1, i, 0)
+        box = x_true +- 0.25, except every 8th parameter: true value exactly on its lower bound;  x0 = box midpoint
+    Recovering 128 decay rates from one noisy curve is ill-posed: measured with this oracle, the reference algorithm exhausts
+    max_inner_iter in every outer iteration on it (which is why BASELINE's cfg2 line uses the channel-separated family above).
+    """
+
+    def __init__(self, M, n, seed=1, noise=1e-3, row0=0, M_total=None):
+        assert n % 2 == 0
+        self.M, self.n, self.seed, self.noise, self.row0 = int(M), int(n), int(seed), noise, int(row0)
+        self.M_total = int(M_total if M_total is not None else M)
+        K = n // 2
+        self.K = K
+        k = np.arange(K, dtype=np.uint64)
+        a = 1.0 + unif(seed, np.zeros(1, dtype=np.uint64), k)[0]
+        b = 0.5 * np.arange(K, dtype=np.float64) + unif(seed, np.ones(1, dtype=np.uint64), k)[0]
+        self.x_true = np.concatenate([a, b])
+        self.xlow = self.x_true - 0.25
+        self.xupp = self.x_true + 0.25
+        on = (np.arange(n) % 8) == 0
+        self.xlow[on] = self.x_true[on]
+        self.xupp[on] = self.x_true[on] + 0.5
+        self.x0 = 0.5 * (self.xlow + self.xupp)
+        i = np.arange(self.row0, self.row0 + self.M, dtype=np.int64)
+        self.t = (i.astype(np.float64) + 0.5) / float(self.M_total)
+        self.y = self._model(self.x_true) + noise * sym(seed + 1, i.astype(np.uint64), np.zeros(1, dtype=np.uint64))[:, 0]
+
+    def _model(self, x):
+        return np.exp(-np.outer(self.t, x[self.K:])) @ x[:self.K]
+
+    def residuals(self, x):
+        return self._model(x) - self.y
+
+    def jac_res(self, x):
+        E = np.exp(-np.outer(self.t, x[self.K:]))
+        return np.hstack([E, -(self.t[:, None] * x[None, :self.K]) * E])
+
+
 def expsum_x_true(n, seed):
     C = n // 2
     c = np.arange(C, dtype=np.uint64)

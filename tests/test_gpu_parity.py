@@ -8,7 +8,7 @@ import pytest
 
 import benlsip_b200 as B
 from oracle import benlsip_oracle as O
-from oracle.models import ExpSumProblem, GlmProblem, MixedConstraintProblem, SphereRegression
+from oracle.models import DenseExpSumProblem, ExpSumProblem, GlmProblem, MixedConstraintProblem, SphereRegression
 
 pytestmark = pytest.mark.gpu
 
@@ -124,7 +124,8 @@ def test_gram_dmma_matches_numpy(S):
 # K11: device models against oracle/models.py
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,Mtot,n,nranks,rank", [("glm", 4096, 64, 1, 0), ("glm", 3001, 250, 1, 0), ("glm", 71500, 1024, 8, 7),
-                                                     ("glm", 9000, 96, 2, 1), ("expsum", 4096, 16, 1, 0), ("expsum", 5140, 64, 4, 2)])
+                                                     ("glm", 9000, 96, 2, 1), ("expsum", 4096, 16, 1, 0), ("expsum", 5140, 64, 4, 2),
+                                                     ("expsum_dense", 4096, 16, 1, 0), ("expsum_dense", 6000, 256, 2, 1)])
 def test_builtin_models_match_oracle(S, kind, Mtot, n, nranks, rank):
     """Rows [row0, row0 + M) of a global problem: the shard of `rank` of `nranks` (bnl_shard_rows)."""
     row0, M = B.shard_rows(Mtot, nranks, rank)
@@ -132,9 +133,13 @@ def test_builtin_models_match_oracle(S, kind, Mtot, n, nranks, rank):
         P = GlmProblem(M, n, seed=3, row0=row0)
         mid = B.MODEL_GLM
         seed = 3
-    else:
+    elif kind == "expsum":
         P = ExpSumProblem(M, n, seed=1, row0=row0, M_total=Mtot)
         mid = B.MODEL_EXPSUM
+        seed = 1
+    else:
+        P = DenseExpSumProblem(M, n, seed=1, row0=row0, M_total=Mtot)
+        mid = B.MODEL_EXPSUM_DENSE
         seed = 1
     S.set_problem(M, n, M_total=Mtot, row0=row0)
     S.use_builtin_model(mid, noise=1e-3, cond_exp=0.0, seed=seed)
@@ -154,7 +159,7 @@ def test_builtin_models_match_oracle(S, kind, Mtot, n, nranks, rank):
     for k in (0, n // 2, n - 1):  # individual columns of J
         e = np.zeros(n)
         e[k] = 1.0
-        assert np.max(np.abs(S.jv(e) - J[:, k])) <= 1e-14 * max(1.0, np.max(np.abs(J[:, k])))
+        assert np.max(np.abs(S.jv(e) - J[:, k])) <= (1e-14 if kind != "expsum_dense" else 1e-13) * max(1.0, np.max(np.abs(J[:, k])))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -359,6 +364,27 @@ def test_expsum_full_solve_parity(S):
     assert abs(tr_g["stats"]["inner_iters"] - tr_o["inner_iters"]) <= 0.15 * tr_o["inner_iters"]
     assert np.max(np.abs(x_g - x_o)) < 1e-8
     assert np.array_equal(tr_g["fixvars_words"], tr_o["fixvars_words"])
+
+
+def test_dense_expsum_first_inner_steps_match_oracle(S):
+    """cfg2 as SURVEY 8d words it (ONE n/2-term exponential sum on one time grid): kappa(J) ~ 1e16 at x0, the reference algorithm
+    does not converge on it (oracle: max_inner_iter exhausted in every outer iteration), so parity is asserted where it is
+    well-posed: model values, the Cauchy step (no CG involved) and the first inner step's counts."""
+    M, n = 4096, 16
+    P = DenseExpSumProblem(M, n, seed=1)
+    S.set_problem(M, n)
+    S.use_builtin_model(B.MODEL_EXPSUM_DENSE, 1e-3, 0.0, 1)
+    x = P.x0.copy()
+    mx, g, _ = S.new_point(x, None, 10.0)
+    J, r = P.jac_res(x), P.residuals(x)
+    assert abs(mx - 0.5 * r @ r) <= 1e-12 * (0.5 * r @ r) and rel(g, J.T @ r) < 1e-11
+    H = O.AlHessian(J, np.zeros((0, n)), 0.0)
+    L0 = O._cholesky_lower(np.zeros((0, 0)))
+    for delta in (1e-3, 0.1):
+        cons = O.MixedConstraints(P.A, L0, l=P.xlow, u=P.xupp)
+        s_ref = O.cauchy_step(x, J.T @ r, H, L0, cons, delta)
+        s = S.cauchy_step(x, J.T @ r, delta)
+        assert rel(s, s_ref) < 1e-9 and np.array_equal(S.fixvars_words(), cons.fixvars_words())
 
 
 def test_sphere_regression_through_callbacks():
