@@ -95,6 +95,8 @@ int bnl_create(int device, bnl_handle* out) {
     {
         const char* env = getenv("BNL_CAUCHY");
         h->cauchy_mode = (env && env[0] == 'l') ? BNL_CAUCHY_LITERAL : BNL_CAUCHY_INCREMENTAL;
+        const char* jt = getenv("BNL_JT");
+        h->jt_disabled = jt && jt[0] == '0';
         const char* fj = getenv("BNL_FUSE_JTR");
         h->fuse_jtr = !(fj && fj[0] == '0');
         const char* gg = getenv("BNL_GRAM_GUARD");
@@ -525,6 +527,7 @@ int bnl_upload_jacobian(bnl_handle h, const double* J_colmajor, int64_t ldj) {
     h->have_J = true;
     h->gram_valid = false;
     h->t0_valid = false;
+    h->jt_valid = h->jt_attempted = false;
     return BNL_OK;
 }
 

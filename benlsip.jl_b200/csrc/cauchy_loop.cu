@@ -85,7 +85,15 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
                         // so four rows are in flight per thread (loads first, then the arithmetic in row order: the per-thread
                         // summation order does not depend on the unrolling).
                         const bool zero_u = (it == zero_u_at);  // u = J s_c = 0 before the first breakpoint
-                        const double* __restrict__ Jc = a.J + ind;
+                        // element (r, ind): from the tile-transposed copy when it exists (16 consecutive rows of a column share a
+                        // 128-byte line, the granularity HBM serves a strided read at: profiles/r2_cauchy_loop_ncu.md), else from
+                        // the row-major Jacobian (one line per row)
+                        const bool tr = a.Jt != nullptr;
+                        const double* __restrict__ Jc = tr ? a.Jt + (size_t)ind * kJtTile : a.J + ind;
+                        const size_t tile_stride = (size_t)a.ld * kJtTile;
+                        auto jelem = [&](long long r) -> double {
+                            return tr ? __ldg(Jc + (size_t)(r >> 4) * tile_stride + (r & 15)) : __ldg(Jc + (size_t)r * a.ld);
+                        };
                         long long i = lb + tid;
                         for (; i + 3 * kCLThreads < le; i += 4 * kCLThreads) {
                             double tv[4], uv[4], jv[4];
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
                                 const long long r = i + (long long)q * kCLThreads;
                                 tv[q] = tp[r];
                                 uv[q] = zero_u ? 0.0 : up[r];
-                                jv[q] = __ldg(Jc + (size_t)r * a.ld);
+                                jv[q] = jelem(r);
                             }
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
                         for (; i < le; i += kCLThreads) {
                             const double t0 = tp[i], u0 = zero_u ? 0.0 : up[i];
                             const double ui = fma(theta, t0, u0);
-                            const double ti = fma(-dind, __ldg(Jc + (size_t)i * a.ld), t0);
+                            const double ti = fma(-dind, jelem(i), t0);
                             tp[i] = ti;
                             up[i] = ui;
                             tt = fma(ti, ti, tt);
@@ -295,6 +303,10 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
                         status = CL_NEED_LITERAL;  // interior minimiser (needs the literal step length) or inside the band
                 }
             }
+            if (advance && a.want_jt && a.q0 + breakpoints >= kJtTrigger) {
+                advance = false;  // a long search: the host builds the tile-transposed copy of J, then re-enters here
+                status = CL_WANT_TRANSPOSE;
+            }
             if (advance) {
                 if (ind < 0)
                     status = CL_ERR_BOUNDS;  // add_active!(ind = -1): BoundsError in the reference (:544, :631)
@@ -338,7 +350,31 @@ __global__ void __launch_bounds__(kCLThreads) k_cauchy_loop(CauchyLoopArgs a) {
     for (int i = tid; i < nw; i += kCLThreads) dsh[i] = s[i];
 }
 
+// Jt[((i/16)*ld + j)*16 + i%16] = J[i][j]: one CTA per 16-row tile; 32 columns at a time go through shared memory, so both the
+// reads (256 B per row) and the writes (the 16 x 32 sub-tile is one contiguous 4 KB block of Jt) are coalesced.
+__global__ void __launch_bounds__(512) k_transpose16(const double* __restrict__ J, long long M, int ld, double* __restrict__ Jt) {
+    __shared__ double tile[kJtTile][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // load: row ty, column tx
+    const int rr = threadIdx.x & 15, cc = threadIdx.x >> 4;        // store: column cc, row rr
+    for (long long tb = blockIdx.x; tb * kJtTile < M; tb += gridDim.x) {
+        const long long r = tb * kJtTile + ty;
+        for (int c0 = 0; c0 < ld; c0 += 32) {
+            tile[ty][tx] = (r < M && c0 + tx < ld) ? J[(size_t)r * ld + c0 + tx] : 0.0;
+            __syncthreads();
+            if (c0 + cc < ld) Jt[((size_t)tb * ld + c0 + cc) * kJtTile + rr] = tile[rr][cc];
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t transpose16_launch(const double* J, long long M, int ld, double* Jt, cudaStream_t st) {
+    long long tiles = (M + kJtTile - 1) / kJtTile;
+    int grid = (int)(tiles < 148 * 16 ? (tiles > 0 ? tiles : 1) : 148 * 16);
+    k_transpose16<<<grid, 512, 0, st>>>(J, M, ld, Jt);
+    return cudaGetLastError();
+}
 
 size_t cauchy_loop_sync_bytes() { return 256; }
 

@@ -391,6 +391,7 @@ int eval_jacobian(S* h, const double* dx, const double* r_for_gradient) {
     h->have_J = true;
     h->gram_valid = false;
     h->t0_valid = false;
+    h->jt_valid = h->jt_attempted = false;
     h->st.jac_eval++;
     if (h->hess_mode == BNL_HESSIAN_GRAM) RET(form_gram(h));
     return BNL_OK;
@@ -480,8 +481,12 @@ int cauchy_step_incremental(S* h, double delta) {
     a.bcast = reinterpret_cast<char*>(h->cl_sync) + 64;
     a.first = 1;
     a.use_literal = 1;  // the first interval is decided with the literal scalars: a search without breakpoints costs one pass
+    int search_bp = 0;
     for (;;) {
         a.ll_epoch0 = h->ll_epoch;
+        a.q0 = search_bp;
+        a.Jt = h->jt_valid ? h->Jt : nullptr;
+        a.want_jt = h->jt_attempted ? 0 : 1;
         CK(cauchy_loop_launch(a, h->prop.multiProcessorCount, h->stream));
         h->st.kernel_launches++;
         h->st.cauchy_loop_launches++;
@@ -489,7 +494,32 @@ int cauchy_step_incremental(S* h, double delta) {
         h->ll_epoch += (unsigned long long)h->sh->cl_rounds;
         h->st.breakpoints += h->sh->cl_breakpoints;
         h->st.inc_breakpoints += h->sh->cl_breakpoints;
+        search_bp += h->sh->cl_breakpoints;
         switch (h->sh->cl_status) {
+            case CL_WANT_TRANSPOSE: {
+                // A long search (>= kJtTrigger breakpoints): every further breakpoint reads one column of J, and HBM serves a strided
+                // 8-byte read with a 128-byte line.  The tile-transposed copy (16 consecutive rows of a column per line) makes the
+                // column read 16 x denser; it costs two passes' worth of traffic once per Jacobian and the same bytes again in HBM,
+                // so it is only built here, and only if the memory is there.  Same values, same arithmetic: bit-identical results.
+                h->jt_attempted = true;  // every rank takes this branch at the same breakpoint, whether or not its copy succeeds
+                if (!h->jt_disabled) {
+                    const size_t bytes = (size_t)((h->M + kJtTile - 1) / kJtTile) * kJtTile * h->ld * sizeof(double);
+                    if (!h->Jt && cudaMalloc(&h->Jt, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+                        cudaGetLastError();
+                        h->Jt = nullptr;
+                        h->jt_disabled = true;
+                    }
+                    if (h->Jt) {
+                        CK(transpose16_launch(h->J, h->M, h->ld, h->Jt, h->stream));
+                        KLAUNCH();
+                        h->jt_valid = true;
+                        h->st.jt_builds++;
+                    }
+                }
+                a.first = 0;
+                a.use_literal = 0;  // re-decide the same breakpoint from the (unchanged) t, u
+                break;
+            }
             case CL_DONE_NOSTEP:
             case CL_DONE_INTERIOR:
             case CL_DONE_EXHAUSTED: return BNL_OK;
@@ -950,6 +980,9 @@ int free_problem(S* h) {
     cudaFree(h->cl_sync);
     cudaFree(h->inc_t0);
     cudaFree(h->hd0);
+    cudaFree(h->Jt);
+    h->Jt = nullptr;
+    h->jt_valid = h->jt_attempted = false;
     h->inc_t = h->inc_u = h->inc_t0 = h->hd0 = nullptr;
     h->t0_valid = false;
     h->cl_sync = nullptr;

@@ -101,6 +101,10 @@ struct bnl_solver {
     double* inc_t0 = nullptr;                    // J P(-g) of the current (x, g, J): reused by the searches after rejected steps
     double* hd0 = nullptr;                       // H P(-g) of the same state (n-vector + norm slot)
     bool t0_valid = false;
+    double* Jt = nullptr;                        // tile-transposed copy of J for long Cauchy searches (built lazily, may stay null)
+    bool jt_valid = false;                       // Jt holds the current J
+    bool jt_attempted = false;                   // a copy was attempted for the current J (uniform across ranks)
+    bool jt_disabled = false;                    // BNL_JT=0, or the allocation failed once
     bool jtr_valid = false;                      // hv = J'r of the Jacobian just generated (fused generator)
     bool fuse_jtr = true;                        // BNL_FUSE_JTR=0 disables the fused generator
     unsigned int* cl_sync = nullptr;             // arrive counter + broadcast record of the persistent loop kernel

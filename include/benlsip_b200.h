@@ -93,6 +93,7 @@ typedef struct bnl_stats {
     double chol_ms;               /* CUDA-event time of the factor rebuilds + downdates                                */
     int64_t fused_jtr;            /* Jacobian generations that produced J'r on the fly (no J'w pass for the gradient)  */
     int64_t gram_breakpoints;     /* Cauchy breakpoints (m_lin > 0) whose Hd came from the Gram matrix (guarded)        */
+    int64_t jt_builds;            /* tile-transposed copies of J built for long Cauchy searches (>= 128 breakpoints)     */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */

@@ -355,3 +355,36 @@ def test_device_cauchy_loop_randomized_equals_literal(S, M, n):
         nbp += sti["breakpoints"]
     assert nbp > n  # the cases did walk breakpoints
     S.set_cauchy_mode(B.CAUCHY_INCREMENTAL)
+
+
+def test_tile_transposed_copy_for_long_searches_is_bit_identical():
+    """A Cauchy search that walks >= 128 breakpoints builds a tile-transposed copy of J (16 consecutive rows of a column per
+    128-byte line) and reads the breakpoint columns from it.  Same values, same arithmetic: step, predicted reduction, active set
+    and the whole solve are bit-identical with the copy disabled (BNL_JT=0) and to the literal search."""
+    import os
+    M, n = 40_000, 700
+    P = GlmProblem(M, n, seed=3)
+    rng = np.random.default_rng(9)
+    x = np.clip(rng.normal(0.0, 0.5, n), -1.0, 1.0)
+    res = []
+    for env in ("1", "0"):
+        os.environ["BNL_JT"] = env
+        try:
+            T = B.Solver(0)
+        finally:
+            del os.environ["BNL_JT"]
+        T.set_problem(M, n)
+        T.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+        mx, g, _ = T.new_point(x, None, 10.0)
+        T.reset_stats()
+        out = [T.inner_step(x, g, d) + (T.fixvars_words(),) for d in (1e-6, 1e-8, 1e-7)]  # tiny radii: hundreds of TR faces each
+        st = T.stats()
+        tr = {}
+        xs, _ = B.tralcnllss(T.model_vectors()["x0"], None, None, None, None, None, None, None, None, solver=T, trace=tr)
+        res.append((out, st, xs, tr))
+        T.close()
+    (oa, sa, xa, ta), (ob, sb, xb, tb) = res
+    assert sa["jt_builds"] >= 1 and sb["jt_builds"] == 0 and sa["breakpoints"] == sb["breakpoints"] > 3 * 128
+    for (s1, p1, w1), (s2, p2, w2) in zip(oa, ob):
+        assert np.array_equal(s1, s2) and p1 == p2 and np.array_equal(w1, w2)
+    assert np.array_equal(xa, xb) and ta["stats"]["breakpoints"] == tb["stats"]["breakpoints"]
