@@ -133,11 +133,18 @@ def _same_log_line(a, b, strict):
         return False
     if not strict:
         return True
-    for u, v in zip(re.findall(_FLOAT, a), re.findall(_FLOAT, b)):
+    fa, fb = re.findall(_FLOAT, a), re.findall(_FLOAT, b)
+    inner_line = re.match(r"^\s*\d+\s+" + _FLOAT, b) is not None
+    for k, (u, v) in enumerate(zip(fa, fb)):
         fu, fv = float(u), float(v)
         digits = len(u.split("e")[0].split(".")[1])
         unit = 10.0 ** (-digits) * 10.0 ** np.floor(np.log10(max(abs(fv), 1e-300)))
-        if abs(fu - fv) > 1.5 * unit and abs(fu - fv) > 1e-12:  # 1e-12 absolute: values that are themselves rounding residue
+        if inner_line and k == len(fb) - 1:
+            # rho = ared / pred (:353-354): ared is a difference of two nearly equal AL values, so before the fragile record
+            # (|ared| >= 256 ulps of mx, tests/parity.py) rho still carries up to ~1 % of rounding noise
+            if abs(fu - fv) > 2e-2 * abs(fv) + 1.5 * unit:
+                return False
+        elif abs(fu - fv) > 1.5 * unit and abs(fu - fv) > 1e-12:  # 1e-12 absolute: values that are themselves rounding residue
             return False
     return True
 
