@@ -400,6 +400,7 @@ def run_ours(args, cfg):
                 cb["extrapolated_full_size_solve_s_same_work"] = ref_passes * cb["s_per_pass_sample"] * (cfg["M"] / cb["sample_rows"])
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
+    barrier()  # no rank frees its peer-mapped mailbox while another one could still be using it
     S.close()
     if world > 1:
         dist.destroy_process_group()
