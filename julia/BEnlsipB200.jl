@@ -52,20 +52,23 @@ mutable struct Solver
     n::Int; M::Int; p::Int; m::Int
     cbs::Any                     # keeps the @cfunction closures alive
     closures::Any                # (residuals, jac_res, nlconstraints, jac_nlcons) currently bound
-    J_id::UInt; C_id::UInt       # objectid of the AlHessian matrices currently on the device
+    J_ref::Any; C_ref::Any       # the AlHessian matrices currently on the device; holding them keeps `===` meaningful (a freed
+                                 # matrix's address can be reused by the next jac_res(x)); in-place edits of H.J need rebind!(H)
     mu::Float64
     function Solver(device::Integer=0)
         hp = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:bnl_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), device, hp)
         rc == 0 || error("bnl_create: " * unsafe_string(ccall((:bnl_status_string, LIB), Cstring, (Cint,), rc)))
-        s = new(hp[], 0, 0, 0, 0, nothing, nothing, UInt(0), UInt(0), NaN)
+        s = new(hp[], 0, 0, 0, 0, nothing, nothing, nothing, nothing, NaN)
         finalizer(s -> ccall((:bnl_destroy, LIB), Cvoid, (Ptr{Cvoid},), s.h), s)
         return s
     end
 end
 
 const DEVICE = Ref(0)
-const SOLVERS = IdDict{Any,Solver}()     # lincons (or an AlHessian used on its own) -> its handle
+# lincons (or an AlHessian used on its own) -> its handle.  Weak keys: both structs are mutable (identity-hashed), and a handle --
+# device buffers included -- is released by its finalizer once the struct it served is garbage
+const SOLVERS = WeakKeyDict{Any,Solver}()
 
 # MixedConstraints(A, cholesky(A*A'); l, u)   src/polyhedral_constraints.jl:9-18, src/basic_tralcnlss.jl:206
 function set_problem!(s::Solver, M::Integer, lincons::MixedConstraints{Float64}, p::Integer)
@@ -75,7 +78,7 @@ function set_problem!(s::Solver, M::Integer, lincons::MixedConstraints{Float64},
         (Ptr{Cvoid}, Int64, Int64, Int64, Int32, Int32, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
         s.h, M, M, 0, n, m, p, m == 0 ? C_NULL : pointer(A), pointer(x_l), pointer(x_u)))
     s.n, s.M, s.p, s.m = n, M, p, m
-    s.J_id = s.C_id = UInt(0)
+    s.J_ref = s.C_ref = nothing
 end
 
 # the handle of `lincons`, created (and dimensioned for M residuals, p nonlinear constraints) on first use
@@ -121,7 +124,7 @@ function use_callbacks!(s::Solver, residuals, jac_res, nlconstraints, jac_nlcons
     s.closures = (residuals, jac_res, nlconstraints, jac_nlcons)
     check(s.h, ccall((:bnl_use_callbacks, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
                      s.h, cbs[1], cbs[2], cbs[3], cbs[4], C_NULL))
-    s.J_id = s.C_id = UInt(0)
+    s.J_ref = s.C_ref = nothing
 end
 
 function set_params!(s::Solver; eta1=0.25, eta2=0.75, gamma1=0.0625, gamma2=2.0, kappa2=0.1, kappa3=0.1,
@@ -139,13 +142,13 @@ set_cauchy_mode!(s::Solver, mode::Int32) = check(s.h, ccall((:bnl_set_cauchy_mod
 
 # ---- AlHessian (src/basic_tralcnlss.jl:6-10): (J, C, mu) uploaded through pinned staging when the struct's matrices change ----
 function bind_hessian!(s::Solver, H::AlHessian{Float64})
-    if objectid(H.J) != s.J_id
+    if H.J !== s.J_ref
         check(s.h, ccall((:bnl_upload_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), s.h, H.J, size(H.J, 1)))
-        s.J_id = objectid(H.J)
+        s.J_ref = H.J
     end
-    if s.p > 0 && objectid(H.C) != s.C_id
+    if s.p > 0 && H.C !== s.C_ref
         check(s.h, ccall((:bnl_upload_nlcons_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), s.h, H.C, size(H.C, 1)))
-        s.C_id = objectid(H.C)
+        s.C_ref = H.C
     end
     if H.mu != s.mu
         check(s.h, ccall((:bnl_set_mu, LIB), Cint, (Ptr{Cvoid}, Cdouble), s.h, H.mu))
@@ -153,6 +156,8 @@ function bind_hessian!(s::Solver, H::AlHessian{Float64})
     end
     return s
 end
+# after H.J or H.C was modified in place: forget the cached matrices so the next call uploads them again
+rebind!(H::AlHessian{Float64}) = (haskey(SOLVERS, H) && (SOLVERS[H].J_ref = SOLVERS[H].C_ref = nothing); H)
 # an AlHessian used on its own (test/structures.jl:1-16): a handle without constraints, keyed by the struct
 function solver_for(H::AlHessian{Float64})
     M, n = size(H.J); p = size(H.C, 1)
@@ -163,7 +168,7 @@ function solver_for(H::AlHessian{Float64})
             (Ptr{Cvoid}, Int64, Int64, Int64, Int32, Int32, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
             s.h, M, M, 0, n, 0, p, C_NULL, lo, up))
         s.n, s.M, s.p, s.m = n, M, p, 0
-        s.J_id = s.C_id = UInt(0)
+        s.J_ref = s.C_ref = nothing
     end
     return bind_hessian!(s, H)
 end
