@@ -314,7 +314,7 @@ def run_ours(args, cfg):
               "jac_eval": st["jac_eval"], "res_eval": st["res_eval"], "j_passes": st["j_passes"],
               "cauchy_loop_launches": st["cauchy_loop_launches"], "cauchy_literal_evals": st["cauchy_literal_evals"],
               "chol_rebuilds": st["chol_rebuilds"], "chol_downdates": st["chol_downdates"], "t0_reuses": st["t0_reuses"],
-              "allreduces": st["allreduces"], "p2p_allreduces": st["p2p_allreduces"],
+              "point_reuses": st["point_reuses"], "allreduces": st["allreduces"], "p2p_allreduces": st["p2p_allreduces"],
               "mu": tr["mu"]}
     phases = {"streaming_kernels_ms": st["hess_mul_ms"] + st["vthv_ms"] + st["jtw_ms"], "jacobian_generation_ms": st["jac_eval_ms"],
               "residual_eval_ms": st["res_eval_ms"], "gram_formation_ms": st["gram_ms"], "projection_factor_ms": st["chol_ms"],
@@ -364,7 +364,9 @@ def run_ours(args, cfg):
                            "collective": ("NVLink peer-memory exchange of per-group sums" if S.comm_info()["p2p_allreduce"] else ("ncclAllGather of per-group sums" if world > 1 else "none")),
                            "l2": f"no flush needed: the J shard streamed by every pass is {8.0 * M_loc * n / 1e9:.1f} GB >> 126 MB L2",
                            "step": "one full tralcnllss solve to the reference tolerances (defaults), outer loop on the host, subproblems through the C ABI",
-                           "hessian": args.hessian, "cauchy": args.cauchy, "iteration_caps": solve_kw or None},
+                           "hessian": args.hessian, "cauchy": args.cauchy, "iteration_caps": solve_kw or None,
+                           "subproblem_restart": ("r, J, J'r reused when a subproblem starts at the x the previous one ended at (bit-identical)"
+                                                  if os.environ.get("BNL_REUSE_POINT", "1")[:1] != "0" else "re-evaluated (BNL_REUSE_POINT=0)")},
                 "counts": counts, "phases_ms_last_step": phases,
                 "final": {"pix": tr["pix"], "nb_fix": int(sum(bin(int(w)).count("1") for w in tr["fixvars_words"])),
                           "x_crc": int(np.frombuffer(x.tobytes(), dtype=np.uint64).sum() & np.uint64(0xFFFFFFFFFFFF))},

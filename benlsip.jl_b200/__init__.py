@@ -72,7 +72,8 @@ class Stats(C.Structure):
                [("kernel_launches", C.c_int64), ("j_passes", C.c_int64), ("gram_count", C.c_int64), ("gram_ms", C.c_double),
                 ("p2p_allreduces", C.c_int64), ("inc_breakpoints", C.c_int64), ("cauchy_loop_launches", C.c_int64),
                 ("cauchy_literal_evals", C.c_int64), ("t0_reuses", C.c_int64), ("chol_downdates", C.c_int64),
-                ("chol_ms", C.c_double), ("fused_jtr", C.c_int64), ("gram_breakpoints", C.c_int64), ("jt_builds", C.c_int64)]
+                ("chol_ms", C.c_double), ("fused_jtr", C.c_int64), ("gram_breakpoints", C.c_int64), ("jt_builds", C.c_int64),
+                ("point_reuses", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

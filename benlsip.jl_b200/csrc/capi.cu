@@ -103,6 +103,8 @@ int bnl_create(int device, bnl_handle* out) {
         if (gg && atof(gg) > 0.0) h->gram_guard = atof(gg);
         const char* gd = getenv("BNL_CAUCHY_GUARD");
         if (gd && atof(gd) > 0.0) h->cauchy_guard = atof(gd);
+        const char* rp = getenv("BNL_REUSE_POINT");
+        h->reuse_point = !(rp && rp[0] == '0');
     }
     cudaEventCreate(&h->ev_t0);
     cudaEventCreate(&h->ev_t1);
@@ -183,6 +185,7 @@ int bnl_comm_init(bnl_handle h, int nranks, int rank, const void* id128) {
     if (kGroups % nranks != 0 || nranks > kP2PMaxRanks)
         return h->fail(BNL_EINVAL, "nranks = %d: the row geometry has %d groups, nranks must be 1, 2, 4 or 8", nranks, kGroups);
     CK(cudaSetDevice(h->device));
+    h->pc_valid = false;
     comm_teardown(h);  // a second call replaces the previous communicator / peer mappings
     h->comm_set = true;
     if (nranks == 1) {
@@ -389,6 +392,7 @@ int bnl_use_builtin_model(bnl_handle h, int32_t model_id, const double* params, 
     if (!valid(h) || !h->problem_set) return BNL_EINVAL;
     if (h->p > 1) return h->fail(BNL_EINVAL, "built-in models support at most one (built-in) nonlinear constraint");
     CK(cudaSetDevice(h->device));
+    h->pc_valid = false;
     const int n = h->n;
     h->seed = seed;
     h->noise = (nparams > 0 && params) ? params[0] : 1e-3;
@@ -474,6 +478,7 @@ int bnl_use_callbacks(bnl_handle h, bnl_callback residuals, bnl_callback jac_res
     if (!valid(h) || !h->problem_set || !residuals || !jac_res) return BNL_EINVAL;
     if (h->p > 0 && (!nlconstraints || !jac_nlcons)) return h->fail(BNL_EINVAL, "p > 0 needs nlconstraints and jac_nlcons");
     h->model_id = 0;
+    h->pc_valid = false;
     h->cb_res = residuals;
     h->cb_jac = jac_res;
     h->cb_nl = nlconstraints;
@@ -489,12 +494,14 @@ int bnl_use_builtin_nlcons(bnl_handle h, int32_t kind, const double* params, int
     if (h->p != 1) return h->fail(BNL_EDIM, "the sphere constraint needs p == 1");
     h->nl_kind = kind;
     h->nl_rho2 = params[0];
+    h->pc_valid = false;
     return BNL_OK;
 }
 
 int bnl_model_set_truth(bnl_handle h, const double* x_true, const double* x0) {
     if (!valid(h) || h->model_id == 0 || !x_true) return BNL_EINVAL;
     CK(cudaSetDevice(h->device));
+    h->pc_valid = false;
     std::copy(x_true, x_true + h->n, h->m_xtrue.begin());
     if (x0) std::copy(x0, x0 + h->n, h->m_x0.begin());
     RET(put_vec(h, h->m_xtrue.data(), h->d_xtrue, h->n));
@@ -515,10 +522,15 @@ int bnl_model_vectors(bnl_handle h, double* x0, double* xlow, double* xupp, doub
     return BNL_OK;
 }
 
+// Every entry point but the two solve calls forgets the point of the last solve's end (solver_internal.h: pc_valid): the reuse
+// at a subproblem restart only ever spans consecutive solve_subproblem calls / the outer iterations of one bnl_tralcnllss.
 #define ENTER()                                                          \
     if (!valid(h)) return BNL_EINVAL;                                    \
     if (!h->problem_set) return h->fail(BNL_EINVAL, "bnl_set_problem first"); \
-    CK(cudaSetDevice(h->device));
+    CK(cudaSetDevice(h->device));                                        \
+    const bool pc_was_valid = h->pc_valid;                               \
+    (void)pc_was_valid;                                                  \
+    h->pc_valid = false;
 
 int bnl_upload_jacobian(bnl_handle h, const double* J_colmajor, int64_t ldj) {
     ENTER();
@@ -933,14 +945,25 @@ static int solve_subproblem_host(bnl_handle h, const double* x0, const double* y
     std::vector<double> yv(h->p, 0.0);
     if (h->p > 0 && y) std::copy(y, y + h->p, yv.begin());
     double px = kInf;
-    int rc = solve_subproblem_dev(h, yv, mu, omega_tol, &px, log);
+    int rc = solve_subproblem_dev(h, yv, mu, omega_tol, &px, log, x0);
     cudaEventRecord(e1, h->stream);
     cudaStreamSynchronize(h->stream);
     float t = 0.f;
     cudaEventElapsedTime(&t, e0, e1);
     h->st.solve_ms += t;
     if (rc != BNL_OK) return rc;
-    if (x) RET(get_vec(h, h->vc.x, x, h->n));
+    if (h->reuse_point && h->model_id != 0) {
+        // the loop leaves r = residuals(x), J = jac_res(x), d_jtr = J'r and cx of its final x in place (a rejected step touches
+        // none of them, an accepted one refreshes all): remember which x that is, bit for bit
+        h->pc_x.resize(h->n);
+        RET(get_vec(h, h->vc.x, h->pc_x.data(), h->n));
+        h->pc_cx = h->h_cx;
+        h->pc_sumsq = h->acc_sumsq;
+        h->pc_valid = true;
+        if (x) std::copy(h->pc_x.begin(), h->pc_x.end(), x);
+    } else if (x) {
+        RET(get_vec(h, h->vc.x, x, h->n));
+    }
     if (cx && h->p > 0) std::copy(h->h_cx.begin(), h->h_cx.end(), cx);
     if (pix) *pix = px;
     return BNL_OK;
@@ -949,6 +972,7 @@ static int solve_subproblem_host(bnl_handle h, const double* x0, const double* y
 int bnl_solve_subproblem(bnl_handle h, const double* x0, const double* y, double mu, double omega_tol, double* x,
                          double* cx, double* pix) {
     ENTER();
+    h->pc_valid = pc_was_valid;
     return solve_subproblem_host(h, x0, y, mu, omega_tol, x, cx, pix, nullptr);
 }
 
@@ -1213,7 +1237,10 @@ int bnl_tralcnllss(bnl_handle h, const double* x0, const bnl_outer_params* op_in
         ++outer_iter;
         h->st.outer_iters++;
         double ss = 0.0;
-        rc = bnl_residuals(h, x.data(), nullptr, &ss);  // objective = dot(rx,rx) :292 -- on every rank, logging or not
+        if (point_hit(h, x.data()))  // x is the point the subproblem just ended at: its dot(rx,rx) is at hand
+            ss = h->pc_sumsq;
+        else
+            rc = bnl_residuals(h, x.data(), nullptr, &ss);  // objective = dot(rx,rx) :292 -- on every rank, logging or not
         if (rc != BNL_OK) break;
         if (log) log_outer(log, outer_iter, ss, feas, mu, pix, omega, false);  // :293
     }

@@ -270,6 +270,7 @@ ModelArgs margs(S* h) {
 // residuals(x) (+ nlconstraints(x) in callback mode).  dx: device x; rbuf: device M.  Leaves global dot(r,r)
 // in sd->sumsq_r (after all-reduce).  c_out: host p-vector.
 int eval_residual(S* h, const double* dx, double* rbuf, std::vector<double>& c_out) {
+    if (rbuf == h->r) h->pc_valid = false;
     c_out.assign(h->p, 0.0);
     if (h->model_id != 0) {
         EvScope ev(h, 3);
@@ -349,6 +350,7 @@ int upload_colmajor(S* h, const double* src, long long rows, int cols, long long
 // jac_res(x), jac_nlcons(x): fills J (and C in callback mode)
 int eval_jacobian(S* h, const double* dx, const double* r_for_gradient) {
     h->jtr_valid = false;
+    h->pc_valid = false;
     if (h->model_id != 0) {
         // first_derivatives (:72-74) computes Jx'*rx right after Jx: when the residual of this x is at hand the GLM generator
         // accumulates J'r while it writes J (bit-identical to a separate J'w pass) and the pass is not streamed back in
@@ -397,16 +399,24 @@ int eval_jacobian(S* h, const double* dx, const double* r_for_gradient) {
     return BNL_OK;
 }
 
-// g = Jx'*rx + Cx'*y_bar  (:45, :74)
+// g = Jx'*rx + Cx'*y_bar  (:45, :74).  The J'r part is kept in d_jtr: a subproblem that restarts from this point takes it from there.
 int gradient(S* h, const double* rbuf, const std::vector<double>& ybar) {
     h->t0_valid = false;
-    if (h->jtr_valid) {  // J'r came out of the Jacobian generation (eval_jacobian): no pass
-        h->jtr_valid = false;
+    const size_t bytes = (size_t)h->ld * sizeof(double);
+    if (!h->d_jtr) CK(cudaMalloc(&h->d_jtr, (size_t)(h->ld + kColAlign) * sizeof(double)));
+    if (h->jtr_cached) {  // new_point at the point of the last solve's end: J'r of this (J, r) is still in d_jtr
+        h->jtr_cached = false;
         h->st.jtw++;
     } else {
-        RET(jtw_dev(h, rbuf, h->vc.hv));
+        if (h->jtr_valid) {  // J'r came out of the Jacobian generation (eval_jacobian): no pass
+            h->jtr_valid = false;
+            h->st.jtw++;
+        } else {
+            RET(jtw_dev(h, rbuf, h->vc.hv));
+        }
+        CK(cudaMemcpyAsync(h->d_jtr, h->vc.hv, bytes, cudaMemcpyDeviceToDevice, h->stream));
     }
-    CK(cudaMemcpyAsync(h->vc.g, h->vc.hv, (size_t)h->ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->vc.g, h->d_jtr, bytes, cudaMemcpyDeviceToDevice, h->stream));
     if (h->p > 0) {
         RET(put_vec(h, ybar.data(), h->vc.pvec, h->p));
         vk_add_Ct(h->vc, h->vc.pvec, h->vc.g, h->stream);
@@ -807,12 +817,38 @@ int set_mu(S* h, double mu) {
     return BNL_OK;
 }
 
-// new_point :32-49 at the x in vc.x
-int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out) {
+bool point_hit(const S* h, const double* x_host) {
+    return x_host && h->reuse_point && h->pc_valid && h->model_id != 0 && h->have_J && (int)h->pc_x.size() == h->n &&
+           std::memcmp(h->pc_x.data(), x_host, (size_t)h->n * sizeof(double)) == 0;
+}
+
+// new_point :32-49 at the x in vc.x (x_host: the same vector on the host, when the caller has it)
+int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out, const double* x_host) {
     VecCtx& c = h->vc;
     h->vc.mu = mu;
-    RET(eval_residual(h, c.x, h->r, h->h_cx));
-    RET(eval_jacobian(h, c.x, h->r));
+    const bool hit = point_hit(h, x_host);
+    h->pc_valid = false;  // from here on h->r / J follow the iterates of this solve
+    double sumsq = 0.0;
+    if (hit) {
+        // residuals(x), jac_res(x), Jx'*rx of a built-in (pure) model at the very point the previous subproblem ended at:
+        // r, J (with its Gram matrix / tile-transposed copy, if formed) and J'r are in HBM, dot(rx,rx) and cx on the host --
+        // the values a re-evaluation would reproduce bit for bit (every kernel on the path is deterministic)
+        h->h_cx = h->pc_cx;
+        sumsq = h->pc_sumsq;
+        if (h->p > 0) {  // built-in jac_nlcons(x): O(n), regenerated (the scaling below depends on mu)
+            if (h->nl_kind != BNL_NLCONS_SPHERE) return h->fail(BNL_EINVAL, "p > 0 with a built-in model needs bnl_use_builtin_nlcons");
+            vk_sphere_jac(h->vc, c.x, h->stream);
+            vk_scale_C(h->vc, h->stream);
+            h->st.kernel_launches += 2;
+        }
+        if (h->hess_mode == BNL_HESSIAN_GRAM && !h->gram_valid) RET(form_gram(h));
+        h->jtr_cached = h->d_jtr != nullptr;
+        h->jtr_valid = false;
+        h->st.point_reuses++;
+    } else {
+        RET(eval_residual(h, c.x, h->r, h->h_cx));
+        RET(eval_jacobian(h, c.x, h->r));
+    }
     if (h->p > 0) {
         vk_scale_C(h->vc, h->stream);
         KLAUNCH();
@@ -823,17 +859,20 @@ int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out) {
     vk_publish(h->sd, h->sh, h->stream);
     KLAUNCH();
     RET(sync(h));
-    *mx_out = al_value(h, h->sh->sumsq_r, y, h->h_cx, mu);
+    if (!hit) sumsq = h->sh->sumsq_r;
+    h->acc_sumsq = sumsq;
+    *mx_out = al_value(h, sumsq, y, h->h_cx, mu);
     return BNL_OK;
 }
 
 
 // ---- solve_subproblem :303-378 ---------------------------------------------------------------------------
 // x0 must already be in vc.x; y on the host.  Leaves x in vc.x, cx in h->h_cx.
-int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double omega_tol, double* pix_out, FILE* log) {
+int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double omega_tol, double* pix_out, FILE* log,
+                         const double* x0_host) {
     VecCtx& c = h->vc;
     double mx = 0.0;
-    RET(new_point(h, y, mu, &mx));  // :332
+    RET(new_point(h, y, mu, &mx, x0_host));  // :332
     vk_pix(c, true, h->stream);     // norm(g) for initial_tr (pix slot ignored here)
     KLAUNCH();
     RET(sync(h));
@@ -850,7 +889,8 @@ int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double o
         vk_publish(h->sd, h->sh, h->stream);
         KLAUNCH();
         RET(sync(h));
-        const double mx_next = al_value(h, h->sh->sumsq_r, y, h->h_cx_next, mu);
+        const double sumsq_next = h->sh->sumsq_r;
+        const double mx_next = al_value(h, sumsq_next, y, h->h_cx_next, mu);
         const double ared = mx_next - mx;
         const double rho = ared / pred;  // NaN when pred == 0 (trap T8)
         bnl_inner_record rec{};
@@ -876,6 +916,7 @@ int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double o
             std::swap(h->r, h->r_trial);
             h->h_cx = h->h_cx_next;
             mx = mx_next;
+            h->acc_sumsq = sumsq_next;
             RET(eval_jacobian(h, c.x, h->r));  // first_derivatives :72 (+ the J'r of :74 on the fly)
             for (int i = 0; i < h->p; ++i) h->h_ybar[i] = y[i] + mu * h->h_cx[i];
             RET(gradient(h, h->r, h->h_ybar));  // :74
@@ -980,6 +1021,9 @@ int free_problem(S* h) {
     cudaFree(h->cl_sync);
     cudaFree(h->inc_t0);
     cudaFree(h->hd0);
+    cudaFree(h->d_jtr);
+    h->d_jtr = nullptr;
+    h->pc_valid = h->jtr_cached = false;
     cudaFree(h->Jt);
     h->Jt = nullptr;
     h->jt_valid = h->jt_attempted = false;

@@ -107,6 +107,16 @@ struct bnl_solver {
     bool jt_disabled = false;                    // BNL_JT=0, or the allocation failed once
     bool jtr_valid = false;                      // hv = J'r of the Jacobian just generated (fused generator)
     bool fuse_jtr = true;                        // BNL_FUSE_JTR=0 disables the fused generator
+    // The point the last solve_subproblem ended at (built-in device models only: pure functions of x).  tralcnllss restarts
+    // the next subproblem from exactly that x whenever the feasibility test passes (:273-283), and residuals(x), jac_res(x)
+    // and Jx'*rx do not depend on (y, mu, omega): r, J and J'r are still in HBM.  pc_valid says that h->r, h->J, d_jtr,
+    // pc_sumsq and pc_cx belong to the host vector pc_x; every entry point other than the two solve calls clears it.
+    bool reuse_point = true;                     // BNL_REUSE_POINT=0: re-evaluate at every subproblem start like the reference
+    bool pc_valid = false;
+    bool jtr_cached = false;                     // gradient(): take J'r from d_jtr (set by new_point on a hit)
+    std::vector<double> pc_x, pc_cx;
+    double pc_sumsq = 0.0, acc_sumsq = 0.0;      // dot(rx,rx) of pc_x / of the current accepted iterate inside a solve
+    double* d_jtr = nullptr;                     // J'r of the last gradient() (ld doubles)
     unsigned int* cl_sync = nullptr;             // arrive counter + broadcast record of the persistent loop kernel
     double cauchy_guard = 1e-9;                  // relative width of the loop's rounding band
     double gram_guard = 1e-7;                    // the same for breakpoints evaluated on the Gram matrix (general projection)
@@ -214,8 +224,10 @@ int gradient(S* h, const double* rbuf, const std::vector<double>& ybar);
 int cauchy_step(S* h, double delta);
 int minor_iterate(S* h, double delta, int* status_out, int* iters_out, bool apply_linesearch_and_accumulate, bool bounds_given);
 int inner_step(S* h, double delta, double* pred_out);
-int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out);
-int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double omega_tol, double* pix_out, FILE* log);
+int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out, const double* x_host = nullptr);
+bool point_hit(const S* h, const double* x_host);  // x_host is bit for bit the point r, J, J'r in HBM were evaluated at
+int solve_subproblem_dev(S* h, const std::vector<double>& y, double mu, double omega_tol, double* pix_out, FILE* log,
+                         const double* x0_host = nullptr);
 int free_problem(S* h);
 void sync_params_to_ctx(S* h);
 inline bool valid(S* h) { return h != nullptr; }

@@ -94,6 +94,8 @@ typedef struct bnl_stats {
     int64_t fused_jtr;            /* Jacobian generations that produced J'r on the fly (no J'w pass for the gradient)  */
     int64_t gram_breakpoints;     /* Cauchy breakpoints (m_lin > 0) whose Hd came from the Gram matrix (guarded)        */
     int64_t jt_builds;            /* tile-transposed copies of J built for long Cauchy searches (>= 128 breakpoints)     */
+    int64_t point_reuses;         /* subproblems that started at the very x the previous one ended at (built-in models): r, J,
+                                     J'r taken from HBM instead of re-evaluated (:332-336); BNL_REUSE_POINT=0 disables          */
 } bnl_stats;
 
 /* One line of the reference's inner-iteration log (print_inner_iter, src/misc.jl:70-80) + extras. */

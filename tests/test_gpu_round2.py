@@ -395,3 +395,59 @@ def test_tile_transposed_copy_for_long_searches_is_bit_identical():
     for (s1, p1, w1), (s2, p2, w2) in zip(oa, ob):
         assert np.array_equal(s1, s2) and p1 == p2 and np.array_equal(w1, w2)
     assert np.array_equal(xa, xb) and ta["stats"]["breakpoints"] == tb["stats"]["breakpoints"]
+
+
+@pytest.mark.parametrize("family", ["glm", "mixed", "glm_native"])
+def test_subproblem_restart_at_the_previous_end_point_is_bit_identical(family, tmp_path):
+    """tralcnllss restarts a subproblem at the very x the previous one returned whenever the feasibility test passes
+    (src/basic_tralcnlss.jl:273-283), and new_point / first_derivatives (:332-336) re-evaluate residuals(x), jac_res(x), Jx'*rx
+    there although none of them depends on (y, mu, omega).  For the built-in (pure) device models the library recognises the
+    point bit for bit and takes r, J (with its Gram matrix / tile-transposed copy) and J'r from HBM.  The whole solve -- x, y, mu,
+    active set, every iteration count, the per-iteration log -- must be bit-identical with the reuse disabled (BNL_REUSE_POINT=0),
+    and the evaluation counters must differ by exactly the number of reuses."""
+    res = []
+    for env in ("1", "0"):
+        os.environ["BNL_REUSE_POINT"] = env
+        try:
+            T = B.Solver(0)
+        finally:
+            del os.environ["BNL_REUSE_POINT"]
+        tr = {}
+        if family == "mixed":
+            P = MixedConstraintProblem(600, 24, 4)
+            T.set_problem(P.M, P.n, P.A, P.xlow, P.xupp, p=1)
+            T.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, P.seed)
+            T.model_set_truth(P.x_star, P.x0)
+            T.use_builtin_nlcons(B.NLCONS_SPHERE, P.rho2)
+            x, y = B.tralcnllss(P.x0, None, None, None, None, None, None, None, None, solver=T, trace=tr, max_outer_iter=60,
+                                max_inner_iter=200)
+            log = ""
+        else:
+            T.set_problem(20_000, 256)
+            T.use_builtin_model(B.MODEL_GLM, 1e-3, 0.0, 3)
+            x0 = T.model_vectors()["x0"]
+            if family == "glm":
+                x, y = B.tralcnllss(x0, None, None, None, None, None, None, None, None, solver=T, trace=tr)
+                log = ""
+            else:  # the outer loop inside the library: the objective of its log line (:292) comes from the same record
+                T.reset_stats()
+                lp = tmp_path / f"log{env}.out"
+                x, y, mu, pix = T.tralcnllss_native(x0, log_path=str(lp))
+                tr = dict(stats=T.stats(), inner=T.inner_log(), fixvars_words=T.fixvars_words(), mu=mu, outer_iters=T.stats()["outer_iters"])
+                log = lp.read_text(encoding="utf-8")
+        res.append((x, y, tr, log))
+        T.close()
+    (xa, ya, ta, la), (xb, yb, tb, lb) = res
+    sa, sb = ta["stats"], tb["stats"]
+    assert sa["point_reuses"] >= 1 and sb["point_reuses"] == 0
+    assert np.array_equal(xa, xb) and np.array_equal(ya, yb) and ta["mu"] == tb["mu"] and la == lb
+    assert np.array_equal(ta["fixvars_words"], tb["fixvars_words"]) and ta["outer_iters"] == tb["outer_iters"]
+    for k in ("inner_iters", "minor_iters", "cg_iters", "breakpoints", "jtw"):
+        assert sa[k] == sb[k], k
+    assert sb["jac_eval"] - sa["jac_eval"] == sa["point_reuses"]
+    assert sb["res_eval"] - sa["res_eval"] >= sa["point_reuses"]
+    ia, ib = ta["inner"], tb["inner"]
+    assert len(ia) == len(ib)
+    for ra, rb in zip(ia, ib):
+        for k in ("k", "nb_fix", "mx", "norm_s", "delta", "rho", "pix", "pred", "bp_cum", "cg_cum"):
+            assert ra[k] == rb[k] or (ra[k] != ra[k] and rb[k] != rb[k]), k
