@@ -214,7 +214,12 @@ int bnl_linesearch(bnl_handle h, const double* g_model, const double* w, const d
 int bnl_inner_step(bnl_handle h, const double* x, const double* g, double delta, double* s, double* pred);
 /* new_point(x,y,mu,...) :32-49 -> mx, g (J, C kept in the handle as H) */
 int bnl_new_point(bnl_handle h, const double* x, const double* y, double mu, double* mx, double* g, double* cx);
-/* solve_subproblem(x0,y,mu,...,omega_tol,...) :303-378 -> (x, cx, pix) */
+/* solve_subproblem(x0,y,mu,...,omega_tol,...) :303-378 -> (x, cx, pix).
+ * With a built-in device model, a call whose x0 equals -- bit for bit -- the x the previous bnl_solve_subproblem on this handle
+ * returned (tralcnllss does exactly that whenever its feasibility test passes, :273-283) does not re-evaluate residuals(x),
+ * jac_res(x), Jx'*rx (:332-336): they are still in device memory and do not depend on (y, mu, omega_tol).  Results are
+ * bit-identical either way; any other entry point in between, or BNL_REUSE_POINT=0 at bnl_create, forces the re-evaluation.
+ * User callbacks are always called.                                                                                       */
 int bnl_solve_subproblem(bnl_handle h, const double* x0, const double* y, double mu, double omega_tol, double* x,
                          double* cx, double* pix);
 /* tralcnllss(x0,...) :167-298 -> (x, y); SURVEY 8f rank 1 (outer loop inside the library; optional:
