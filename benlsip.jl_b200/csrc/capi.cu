@@ -938,6 +938,7 @@ int bnl_new_point(bnl_handle h, const double* x, const double* y, double mu, dou
 static int solve_subproblem_host(bnl_handle h, const double* x0, const double* y, double mu, double omega_tol, double* x,
                                  double* cx, double* pix, FILE* log) {
     if (!x0) return BNL_EINVAL;
+    h->t0_carry = h->t0_valid;
     h->t0_valid = false;
     cudaEvent_t e0 = h->ev_t0, e1 = h->ev_t1;
     RET(put_vec(h, x0, h->vc.x, h->n));

@@ -856,6 +856,10 @@ int new_point(S* h, const std::vector<double>& y, double mu, double* mx_out, con
     h->h_ybar.resize(h->p);
     for (int i = 0; i < h->p; ++i) h->h_ybar[i] = y[i] + mu * h->h_cx[i];  // :43
     RET(gradient(h, h->r, h->h_ybar));                                     // :45
+    // Without nonlinear constraints g = J'r and H = J'J are those of the previous subproblem's end as well: if its last step was
+    // rejected, Hd = H*P(-g) and t = J P(-g) of the first Cauchy interval (:609) are still the right ones (cauchy_step_incremental)
+    if (hit && h->p == 0 && h->t0_carry) h->t0_valid = true;
+    h->t0_carry = false;
     vk_publish(h->sd, h->sh, h->stream);
     KLAUNCH();
     RET(sync(h));

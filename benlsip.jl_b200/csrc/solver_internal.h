@@ -101,6 +101,7 @@ struct bnl_solver {
     double* inc_t0 = nullptr;                    // J P(-g) of the current (x, g, J): reused by the searches after rejected steps
     double* hd0 = nullptr;                       // H P(-g) of the same state (n-vector + norm slot)
     bool t0_valid = false;
+    bool t0_carry = false;                       // t0_valid as the previous solve_subproblem left it (see new_point)
     double* Jt = nullptr;                        // tile-transposed copy of J for long Cauchy searches (built lazily, may stay null)
     bool jt_valid = false;                       // Jt holds the current J
     bool jt_attempted = false;                   // a copy was attempted for the current J (uniform across ranks)

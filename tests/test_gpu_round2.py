@@ -445,6 +445,7 @@ def test_subproblem_restart_at_the_previous_end_point_is_bit_identical(family, t
     for k in ("inner_iters", "minor_iters", "cg_iters", "breakpoints", "jtw"):
         assert sa[k] == sb[k], k
     assert sb["jac_eval"] - sa["jac_eval"] == sa["point_reuses"]
+    assert sa["t0_reuses"] >= sb["t0_reuses"] and sa["hess_mul"] == sb["hess_mul"] and sa["j_passes"] <= sb["j_passes"]
     assert sb["res_eval"] - sa["res_eval"] >= sa["point_reuses"]
     ia, ib = ta["inner"], tb["inner"]
     assert len(ia) == len(ib)
