@@ -63,3 +63,45 @@ def test_status_strings():
     lib = B.load_library()
     assert b"PosDef" in lib.bnl_status_string(-6)
     assert b"no CPU path" in lib.bnl_status_string(-9)
+
+
+def test_every_entry_point_rejects_a_null_handle():
+    """No entry point dereferences a NULL handle: BNL_EINVAL (-1) from every int-returning function, a message from
+    bnl_last_error, nothing from bnl_destroy.  (No device needed: the guard is the first statement of every function.)"""
+    import ctypes as C
+
+    lib = B.load_library()
+    checked = 0
+    for name, (argtypes, restype) in sorted(lib._bnl_signatures.items()):
+        if not argtypes or argtypes[0] is not C.c_void_p or name == "bnl_comm_unique_id":
+            continue
+        args = []
+        for t in argtypes:
+            if t in (C.c_void_p, C.c_char_p) or (hasattr(t, "_type_") and not isinstance(t._type_, str)):
+                args.append(None)
+            elif t is B.CALLBACK:
+                args.append(B.CALLBACK(0))
+            elif t is C.c_double:
+                args.append(0.0)
+            else:
+                args.append(0)
+        r = getattr(lib, name)(*args)
+        if restype is C.c_int:
+            assert r == -1, f"{name}(NULL, ...) returned {r}"
+        elif restype is C.c_char_p:
+            assert r
+        checked += 1
+    assert checked >= 45
+
+
+def test_create_without_a_device_reports_enodev():
+    import ctypes as C
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = B.load_library()
+    h = C.c_void_p()
+    rc = lib.bnl_create(0, C.byref(h))
+    assert rc == -9 and not h.value and b"no CPU path" in lib.bnl_status_string(rc)
