@@ -189,7 +189,7 @@ def test_native_log_equals_the_oracle_log(S, tmp_path, case):
     assert rel(x_n, x_o) < (1e-10 if F is None else 2e-8)
 
 
-@pytest.mark.parametrize("M", [200_000, 500_000])
+@pytest.mark.parametrize("M", [200_000, 500_000, 1_000_000])
 def test_headline_regime_against_golden(S, M):
     """cfg3's regime at sizes the oracle finishes once on the host (n = 1024, M/n = 200 and 500: hundreds of Cauchy breakpoints,
     projected CG all but absent at 5e5): the trajectory against the committed golden (tests/golden/make_golden_headline.py) --

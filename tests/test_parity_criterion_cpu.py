@@ -26,7 +26,7 @@ def test_fragile_rules():
 
 
 def test_goldens_have_a_substantial_exact_prefix():
-    for name in ["glm_4096_64", "glm_20000_256", "glm_6000_1024", "glm_200000_1024", "glm_500000_1024", "mixed_600_24_4",
+    for name in ["glm_4096_64", "glm_20000_256", "glm_6000_1024", "glm_200000_1024", "glm_500000_1024", "glm_1000000_1024", "mixed_600_24_4",
                  "mixed_4000_64_8", "mixed_20000_256_16"]:
         g = golden(name)
         F = first_fragile(g)
