@@ -31,3 +31,31 @@ def test_reference_arm_line_and_thread_count():
 
 def test_reference_arm_other_ranks_exit_without_work():
     assert _run({"RANK": "3", "WORLD_SIZE": "8"}) == ""
+
+
+def test_prefix_agreement_report():
+    """bench.py's `same_problem` leg states where the CPU port's own trajectory becomes noise-driven and whether the GPU trajectory
+    equals it exactly up to there (the criterion of tests/parity.py): identical traces agree; a trace that differs inside the
+    compared prefix does not; one that differs only after it still does."""
+    import copy
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    from tests.parity import golden
+    g = golden("glm_200000_1024")
+    rep = bench.prefix_agreement(g, g["inner"])
+    F = rep["cpu_trace_noise_driven_from_inner_record"]
+    assert rep["exact_prefix_equal"] and F is not None and rep["records_compared_exactly"] == F >= 5
+    bad = copy.deepcopy(g["inner"])
+    bad[2]["bp_cum"] += 1
+    assert not bench.prefix_agreement(g, bad)["exact_prefix_equal"]
+    tail = copy.deepcopy(g["inner"])[: F + 1]
+    tail[F]["bp_cum"] += 7
+    assert bench.prefix_agreement(g, tail)["exact_prefix_equal"]
+    assert not bench.prefix_agreement(g, g["inner"][: F - 1])["exact_prefix_equal"]
